@@ -1,0 +1,312 @@
+// dvf_warp.cu -- the drop-in inverse_warp operator (materialised warped image) and its backward,
+// plus the reference's stand-alone pixel2cam / cam2pixel.
+//
+// Replaces pytorch_version/inverse_warp.py: pixel2cam :26-40, cam2pixel :43-74, inverse_warp
+// :160-193 (and F.grid_sample's grid_sampler_2d forward/backward, which the reference calls at
+// :191).  The reference runs a K=3 bmm, ~25 elementwise kernels and a sampler per call; here one
+// kernel per direction: thread = target pixel, every per-pixel load/store is coalesced, the 4
+// bilinear taps per channel are read-only gathers served by L1/L2.
+#include "dvf_internal.h"
+#include "dvf_math.cuh"
+#include "dvf_reduce.cuh"
+
+namespace dvf {
+
+struct WarpParams {
+  int B, C, H, W, HW;
+  FastDiv divW;
+  float fW1, fH1, rW1, rH1, halfW, halfH;
+  int allow_fast, zeros_padding;
+  int blocks_per_image;
+  const float* img;
+  const float* depth;
+  const float* P;
+  const float* Kinv;
+  // forward
+  float* warped;
+  uint8_t* valid;
+  // backward
+  const float* gout;
+  float* gdepth;
+  float* gP;
+  float* gimg;
+  float* partials;        // [B*blocks_per_image][kRedSlots]
+  unsigned* img_counter;  // [B]
+};
+
+constexpr int kWarpPPT = 2;
+
+__device__ __forceinline__ void load_PM(const WarpParams& p, int b, float (&P)[12], float (&M)[9]) {
+#pragma unroll
+  for (int k = 0; k < 12; ++k) P[k] = __ldg(p.P + b * 12 + k);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) M[k] = __ldg(p.Kinv + b * 9 + k);
+}
+
+__global__ void __launch_bounds__(kThreads) inverse_warp_fwd_kernel(const __grid_constant__ WarpParams p) {
+  const int b = blockIdx.x / p.blocks_per_image;
+  const int chunk = blockIdx.x - b * p.blocks_per_image;
+  float P[12], M[9];
+  load_PM(p, b, P, M);
+  const int HW = p.HW, W = p.W, H = p.H;
+  const float* img_b = p.img + (size_t)b * p.C * HW;
+  float* out_b = p.warped + (size_t)b * p.C * HW;
+  const bool zeros = p.zeros_padding != 0;
+#pragma unroll
+  for (int q = 0; q < kWarpPPT; ++q) {
+    const int idx = chunk * (kThreads * kWarpPPT) + q * kThreads + threadIdx.x;
+    if (idx >= HW) continue;
+    const int i = (int)fastdiv((uint32_t)idx, p.divW), j = idx - i * W;
+    Cam cam;
+    Proj pr;
+    Loc L;
+    pixel_to_cam(M, ld_stream(p.depth + (size_t)b * HW + idx), i, j, cam);
+    if (zeros) {
+      project<true>(P, cam, p.fW1, p.fH1, p.rW1, p.rH1, p.allow_fast != 0, pr);
+      locate<true>(pr.xn, pr.yn, H, W, p.halfW, p.halfH, L);
+    } else {
+      project<false>(P, cam, p.fW1, p.fH1, p.rW1, p.rH1, p.allow_fast != 0, pr);
+      locate<false>(pr.xn, pr.yn, H, W, p.halfW, p.halfH, L);
+    }
+    const int o_nw = L.y0 * W + L.x0;
+    const float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
+    bool any = false;
+    for (int c = 0; c < p.C; ++c) {
+      const float* pl = img_b + (size_t)c * HW + o_nw;
+      const float a0 = L.bnw ? __ldg(pl) : 0.0f, a1 = L.bne ? __ldg(pl + 1) : 0.0f;
+      const float a2 = L.bsw ? __ldg(pl + W) : 0.0f, a3 = L.bse ? __ldg(pl + W + 1) : 0.0f;
+      const float wv = bilerp(a0, a1, a2, a3, wnw, wne, wsw, wse);
+      any |= (wv != 0.0f);
+      st_stream(out_b + (size_t)c * HW + idx, wv);
+    }
+    if (p.valid) p.valid[(size_t)b * HW + idx] = any ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) inverse_warp_bwd_kernel(const __grid_constant__ WarpParams p) {
+  __shared__ float s_red[kThreads / 32][kRedSlots];
+  __shared__ int s_flag;
+  const int b = blockIdx.x / p.blocks_per_image;
+  const int chunk = blockIdx.x - b * p.blocks_per_image;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float P[12], M[9];
+  load_PM(p, b, P, M);
+  const int HW = p.HW, W = p.W, H = p.H;
+  const float* img_b = p.img + (size_t)b * p.C * HW;
+  const float* gout_b = p.gout + (size_t)b * p.C * HW;
+  float* gimg_b = p.gimg ? p.gimg + (size_t)b * p.C * HW : nullptr;
+  const bool zeros = p.zeros_padding != 0;
+  float acc[kRedSlots];
+#pragma unroll
+  for (int k = 0; k < kRedSlots; ++k) acc[k] = 0.0f;
+
+#pragma unroll
+  for (int q = 0; q < kWarpPPT; ++q) {
+    const int idx = chunk * (kThreads * kWarpPPT) + q * kThreads + tid;
+    if (idx >= HW) continue;
+    const int i = (int)fastdiv((uint32_t)idx, p.divW), j = idx - i * W;
+    Cam cam;
+    Proj pr;
+    Loc L;
+    pixel_to_cam(M, ld_stream(p.depth + (size_t)b * HW + idx), i, j, cam);
+    if (zeros) {
+      project<true>(P, cam, p.fW1, p.fH1, p.rW1, p.rH1, p.allow_fast != 0, pr);
+      locate<true>(pr.xn, pr.yn, H, W, p.halfW, p.halfH, L);
+    } else {
+      project<false>(P, cam, p.fW1, p.fH1, p.rW1, p.rH1, p.allow_fast != 0, pr);
+      locate<false>(pr.xn, pr.yn, H, W, p.halfW, p.halfH, L);
+    }
+    const int o_nw = L.y0 * W + L.x0;
+    const float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
+    float gx = 0.0f, gy = 0.0f;
+    for (int c = 0; c < p.C; ++c) {
+      const float* pl = img_b + (size_t)c * HW + o_nw;
+      const float g = ld_stream(gout_b + (size_t)c * HW + idx);
+      const float a0 = L.bnw ? __ldg(pl) : 0.0f, a1 = L.bne ? __ldg(pl + 1) : 0.0f;
+      const float a2 = L.bsw ? __ldg(pl + W) : 0.0f, a3 = L.bse ? __ldg(pl + W + 1) : 0.0f;
+      bilerp_grad(a0, a1, a2, a3, L, g, gx, gy);
+      if (gimg_b) {
+        float* gp = gimg_b + (size_t)c * HW + o_nw;
+        if (L.bnw) atomicAdd(gp, mul(wnw, g));
+        if (L.bne) atomicAdd(gp + 1, mul(wne, g));
+        if (L.bsw) atomicAdd(gp + W, mul(wsw, g));
+        if (L.bse) atomicAdd(gp + W + 1, mul(wse, g));
+      }
+    }
+    ChainGrad cg;
+    chain_backward(P, cam, pr, L, gx, gy, p.fW1, p.fH1, p.rW1, p.rH1, cg);
+    st_stream(p.gdepth + (size_t)b * HW + idx, cg.gdepth);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc[r * 4 + k] = fmaf(cg.gq[r], cam.cam[k], acc[r * 4 + k]);
+      acc[r * 4 + 3] += cg.gq[r];
+    }
+  }
+
+  const float r = butterfly16(acc, lane);
+  if ((lane & 1) == 0) s_red[warp][butterfly_slot(lane)] = r;
+  __syncthreads();
+  if (tid < kRedSlots) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w8 = 0; w8 < kThreads / 32; ++w8) t += s_red[w8][tid];
+    __stcg(p.partials + (size_t)blockIdx.x * kRedSlots + tid, t);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_flag = (atomicAdd(p.img_counter + b, 1u) == (unsigned)(p.blocks_per_image - 1));
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  const float* img_part = p.partials + (size_t)b * p.blocks_per_image * kRedSlots;
+  if (tid < 12 * 8) {
+    const int s = tid >> 3;
+    const double sum = group8_sum(img_part + s, p.blocks_per_image, kRedSlots, tid & 7);
+    if ((tid & 7) == 0) p.gP[(size_t)b * 12 + s] = (float)sum;
+  }
+  if (tid == 0) p.img_counter[b] = 0u;
+}
+
+// ---- stand-alone pixel2cam / cam2pixel ---------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) pixel2cam_kernel(const float* __restrict__ depth,
+                                                             const float* __restrict__ Kinv, int HW, FastDiv divW,
+                                                             int W, float* __restrict__ cam) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= HW) return;
+  float M[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) M[k] = __ldg(Kinv + b * 9 + k);
+  const int i = (int)fastdiv((uint32_t)idx, divW), j = idx - i * W;
+  Cam c;
+  pixel_to_cam(M, depth[(size_t)b * HW + idx], i, j, c);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) cam[((size_t)b * 3 + k) * HW + idx] = c.cam[k];
+}
+
+__global__ void __launch_bounds__(kThreads) cam2pixel_kernel(const float* __restrict__ cam, const float* __restrict__ rot,
+                                                             const float* __restrict__ tr, int H, int W, int HW,
+                                                             int zeros, float* __restrict__ grid) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= HW) return;
+  float c[3], q[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c[k] = cam[((size_t)b * 3 + k) * HW + idx];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    // inverse_warp.py:54-60: both the rotation and the translation are optional
+    float v = rot ? dot3(__ldg(rot + b * 9 + k * 3), __ldg(rot + b * 9 + k * 3 + 1), __ldg(rot + b * 9 + k * 3 + 2), c[0], c[1], c[2])
+                  : c[k];
+    q[k] = tr ? add(v, __ldg(tr + b * 3 + k)) : v;
+  }
+  const float Z = (q[2] < kMinDepthZ) ? kMinDepthZ : q[2];
+  float xn = sub(div(mul(2.0f, div(q[0], Z)), (float)(W - 1)), 1.0f);
+  float yn = sub(div(mul(2.0f, div(q[1], Z)), (float)(H - 1)), 1.0f);
+  if (zeros) {
+    if (xn > 1.0f || xn < -1.0f) xn = 2.0f;
+    if (yn > 1.0f || yn < -1.0f) yn = 2.0f;
+  }
+  reinterpret_cast<float2*>(grid)[(size_t)b * HW + idx] = make_float2(xn, yn);
+}
+
+static int fill_params(const dvf_desc* d, WarpParams& p) {
+  if (!d) return DVF_EINVAL_NULL;
+  if (d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0 || (long long)d->H * d->W >= (1ll << 30)) return DVF_EINVAL_SHAPE;
+  if (d->padding != DVF_PAD_ZEROS && d->padding != DVF_PAD_BORDER) return DVF_EINVAL_DTYPE;
+  if (d->dtype != DVF_F32 && d->dtype != DVF_BF16) return DVF_EINVAL_DTYPE;
+  if (d->layout != DVF_NCHW && d->layout != DVF_NHWC) return DVF_EINVAL_DTYPE;
+  if (d->dtype != DVF_F32 || d->layout != DVF_NCHW) return DVF_EUNSUPPORTED;
+  p.B = d->B;
+  p.C = d->C;
+  p.H = d->H;
+  p.W = d->W;
+  p.HW = d->H * d->W;
+  p.divW = make_fastdiv((uint32_t)d->W);
+  p.fW1 = (float)(d->W - 1);
+  p.fH1 = (float)(d->H - 1);
+  p.allow_fast = d->W > 1 && d->H > 1;
+  p.rW1 = p.allow_fast ? (float)(1.0 / (double)p.fW1) : 0.0f;
+  p.rH1 = p.allow_fast ? (float)(1.0 / (double)p.fH1) : 0.0f;
+  p.halfW = (float)d->W / 2.0f;
+  p.halfH = (float)d->H / 2.0f;
+  p.zeros_padding = d->padding == DVF_PAD_ZEROS;
+  p.blocks_per_image = (p.HW + kThreads * kWarpPPT - 1) / (kThreads * kWarpPPT);
+  return DVF_OK;
+}
+
+}  // namespace dvf
+
+using namespace dvf;
+
+DVF_EXPORT int dvf_inverse_warp_fwd(const dvf_desc* d, const void* img, const float* depth, const float* P,
+                                    const float* Kinv, void* warped, uint8_t* valid, void* stream) {
+  WarpParams p = {};
+  int st = fill_params(d, p);
+  if (st != DVF_OK) return st;
+  if (!img || !depth || !P || !Kinv || !warped) return DVF_EINVAL_NULL;
+  if (!aligned(img, 4) || !aligned(depth, 4) || !aligned(P, 4) || !aligned(Kinv, 4) || !aligned(warped, 4)) return DVF_EINVAL_ALIGN;
+  p.img = static_cast<const float*>(img);
+  p.depth = depth;
+  p.P = P;
+  p.Kinv = Kinv;
+  p.warped = static_cast<float*>(warped);
+  p.valid = valid;
+  inverse_warp_fwd_kernel<<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return launch_status();
+}
+
+DVF_EXPORT size_t dvf_inverse_warp_bwd_workspace_bytes(const dvf_desc* d) {
+  WarpParams p = {};
+  if (fill_params(d, p) != DVF_OK) return 0;
+  return align_up((size_t)p.blocks_per_image * p.B * kRedSlots * sizeof(float), 256) + align_up((size_t)p.B * sizeof(unsigned), 256);
+}
+
+DVF_EXPORT int dvf_inverse_warp_bwd(const dvf_desc* d, const void* gout, const void* img, const float* depth,
+                                    const float* P, const float* Kinv, float* gdepth, float* gP, void* gimg,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  WarpParams p = {};
+  int st = fill_params(d, p);
+  if (st != DVF_OK) return st;
+  if (!gout || !img || !depth || !P || !Kinv || !gdepth || !gP) return DVF_EINVAL_NULL;
+  if (!aligned(gout, 4) || !aligned(img, 4) || !aligned(depth, 4) || !aligned(gdepth, 4) || !aligned(gP, 4)) return DVF_EINVAL_ALIGN;
+  const size_t need = dvf_inverse_warp_bwd_workspace_bytes(d);
+  if (!workspace || workspace_bytes < need) return DVF_EWORKSPACE;
+  if (!aligned(workspace, 256)) return DVF_EINVAL_ALIGN;
+  p.img = static_cast<const float*>(img);
+  p.gout = static_cast<const float*>(gout);
+  p.depth = depth;
+  p.P = P;
+  p.Kinv = Kinv;
+  p.gdepth = gdepth;
+  p.gP = gP;
+  p.gimg = static_cast<float*>(gimg);
+  p.partials = static_cast<float*>(workspace);
+  p.img_counter = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) +
+                                              align_up((size_t)p.blocks_per_image * p.B * kRedSlots * sizeof(float), 256));
+  inverse_warp_bwd_kernel<<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return launch_status();
+}
+
+DVF_EXPORT int dvf_pixel2cam(const float* depth, const float* Kinv, int32_t B, int32_t H, int32_t W, float* cam,
+                             void* stream) {
+  if (!depth || !Kinv || !cam) return DVF_EINVAL_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || (long long)H * W >= (1ll << 30)) return DVF_EINVAL_SHAPE;
+  const int HW = H * W;
+  dim3 grid((HW + kThreads - 1) / kThreads, B);
+  pixel2cam_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(depth, Kinv, HW, make_fastdiv((uint32_t)W), W, cam);
+  return launch_status();
+}
+
+DVF_EXPORT int dvf_cam2pixel(const float* cam, const float* rot, const float* tr, int32_t B, int32_t H, int32_t W,
+                             int32_t padding, float* grid_out, void* stream) {
+  if (!cam || !grid_out) return DVF_EINVAL_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || (long long)H * W >= (1ll << 30)) return DVF_EINVAL_SHAPE;
+  if (padding != DVF_PAD_ZEROS && padding != DVF_PAD_BORDER) return DVF_EINVAL_DTYPE;
+  if (!aligned(grid_out, 8)) return DVF_EINVAL_ALIGN;
+  const int HW = H * W;
+  dim3 grid((HW + kThreads - 1) / kThreads, B);
+  cam2pixel_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(cam, rot, tr, H, W, HW, padding == DVF_PAD_ZEROS, grid_out);
+  return launch_status();
+}

@@ -1,0 +1,368 @@
+"""torch.autograd bindings of the CUDA operators in libdvf_b200.so.
+
+PyTorch is used for device memory, streams and autograd plumbing only: every tensor handed to
+the library is a raw data_ptr(), every launch goes to torch's current CUDA stream.  There is no
+CPU path -- tensors that are not on a CUDA device raise DvfError.
+
+Reference functions replaced (pytorch_version/): inverse_warp.py:26-193 and the
+photometric_reconstruction_loss variants of loss_functions.py:7-20, loss_functions_sfm.py:9-46,
+loss_function_sfm_old.py:7-46.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import DvfError, PADDING, ROTATION, dvf_desc, dvf_level, dvf_loss_desc
+
+_WS = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t, name, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise DvfError(f"{name} is on {t.device}: dvf_b200 is CUDA-only (sm_100a); there is no CPU fallback")
+    if t.dtype != torch.float32:
+        raise DvfError(f"{name}: dtype {t.dtype} not supported by this entry (float32 expected)")
+    if ndim is not None and t.dim() != ndim:
+        raise AssertionError(f"wrong size for {name}, expected {ndim} dims, got {list(t.size())}")
+    return t.contiguous()
+
+
+def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Zero-initialised scratch, one per (device, stream); the kernels keep it reusable."""
+    key = (device.index, _stream())
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------------
+# pose -> projection
+# ------------------------------------------------------------------------------------------------
+def pose_proj_fwd(vec, K, Kinv, V, rotation_mode, downscales: Sequence[float], want_posemat=False):
+    """vec [B*V,6] (b-major) -> (posemat [B*V,3,4] | None, P [L,B*V,3,4] | None, Kinv_s [L,B,3,3] | None)."""
+    lib = _lib.load()
+    n = vec.shape[0]
+    B = n // V
+    L = len(downscales)
+    dev = vec.device
+    posemat = torch.empty(n, 3, 4, device=dev, dtype=torch.float32) if (want_posemat or K is None) else None
+    P = torch.empty(L, n, 3, 4, device=dev, dtype=torch.float32) if (K is not None and L) else None
+    Ks = torch.empty(L, B, 3, 3, device=dev, dtype=torch.float32) if (Kinv is not None and L) else None
+    ds = (C.c_float * max(L, 1))(*[float(d) for d in downscales])
+    _lib.check(lib.dvf_pose_proj_fwd(_ptr(vec), _ptr(K), _ptr(Kinv), B, V, ROTATION[rotation_mode], ds, L,
+                                     _ptr(posemat), _ptr(P), _ptr(Ks), _stream()), "dvf_pose_proj_fwd")
+    return posemat, P, Ks
+
+
+def pose_proj_bwd(gP, gposemat, vec, K, V, rotation_mode, downscales: Sequence[float]):
+    lib = _lib.load()
+    n = vec.shape[0]
+    L = len(downscales)
+    gvec = torch.empty(n, 6, device=vec.device, dtype=torch.float32)
+    ds = (C.c_float * max(L, 1))(*[float(d) for d in downscales])
+    _lib.check(lib.dvf_pose_proj_bwd(_ptr(gP), _ptr(gposemat), _ptr(vec), _ptr(K), n // V, V, ROTATION[rotation_mode],
+                                     ds, L, _ptr(gvec), _stream()), "dvf_pose_proj_bwd")
+    return gvec
+
+
+class PoseVec2Mat(torch.autograd.Function):
+    """pose_vec2mat (inverse_warp.py:141-157) with analytic backward."""
+
+    @staticmethod
+    def forward(ctx, vec, rotation_mode):
+        vec = _req(vec, "vec", 2)
+        posemat, _, _ = pose_proj_fwd(vec, None, None, 1, rotation_mode, [], want_posemat=True)
+        ctx.save_for_backward(vec)
+        ctx.rotation_mode = rotation_mode
+        return posemat
+
+    @staticmethod
+    def backward(ctx, g):
+        (vec,) = ctx.saved_tensors
+        return pose_proj_bwd(None, _req(g, "grad"), vec, None, 1, ctx.rotation_mode, []), None
+
+
+# ------------------------------------------------------------------------------------------------
+# inverse_warp
+# ------------------------------------------------------------------------------------------------
+def _desc(img, padding_mode):
+    B, Cc, H, W = img.shape
+    return dvf_desc(B, Cc, H, W, _lib.F32, _lib.NCHW, PADDING[padding_mode], 0)
+
+
+def inverse_warp_fwd_P(img, depth, P, Kinv, padding_mode="zeros", want_valid=False):
+    """Non-autograd forward given P = K @ pose_vec2mat(pose) [B,3,4]."""
+    lib = _lib.load()
+    img, depth, P, Kinv = _req(img, "img", 4), _req(depth, "depth", 3), _req(P, "P", 3), _req(Kinv, "intrinsics_inv", 3)
+    warped = torch.empty_like(img)
+    valid = torch.empty(depth.shape, dtype=torch.uint8, device=img.device) if want_valid else None
+    d = _desc(img, padding_mode)
+    _lib.check(lib.dvf_inverse_warp_fwd(C.byref(d), _ptr(img), _ptr(depth), _ptr(P), _ptr(Kinv), _ptr(warped),
+                                        _ptr(valid), _stream()), "dvf_inverse_warp_fwd")
+    return (warped, valid) if want_valid else warped
+
+
+def inverse_warp_bwd_P(gout, img, depth, P, Kinv, padding_mode="zeros", need_gimg=True):
+    """Non-autograd backward: returns (gimg | None, gdepth, gP[B,3,4])."""
+    lib = _lib.load()
+    gout, img, depth, P, Kinv = (_req(gout, "grad_output", 4), _req(img, "img", 4), _req(depth, "depth", 3),
+                                 _req(P, "P", 3), _req(Kinv, "intrinsics_inv", 3))
+    d = _desc(img, padding_mode)
+    gdepth = torch.empty_like(depth)
+    gP = torch.empty(img.shape[0], 3, 4, device=img.device, dtype=torch.float32)
+    gimg = torch.zeros_like(img) if need_gimg else None
+    nbytes = lib.dvf_inverse_warp_bwd_workspace_bytes(C.byref(d))
+    ws = workspace(nbytes, img.device)
+    _lib.check(lib.dvf_inverse_warp_bwd(C.byref(d), _ptr(gout), _ptr(img), _ptr(depth), _ptr(P), _ptr(Kinv),
+                                        _ptr(gdepth), _ptr(gP), _ptr(gimg), _ptr(ws), ws.numel(), _stream()),
+               "dvf_inverse_warp_bwd")
+    return gimg, gdepth, gP
+
+
+class InverseWarp(torch.autograd.Function):
+    """inverse_warp (inverse_warp.py:160-193): differentiable w.r.t. img, depth and pose."""
+
+    @staticmethod
+    def forward(ctx, img, depth, pose, intrinsics, intrinsics_inv, rotation_mode, padding_mode):
+        img, depth, pose = _req(img, "img", 4), _req(depth, "depth", 3), _req(pose, "pose", 2)
+        K, Kinv = _req(intrinsics, "intrinsics", 3), _req(intrinsics_inv, "intrinsics_inv", 3)
+        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+            raise DvfError("gradients w.r.t. the camera intrinsics are not implemented (unused by the reference)")
+        _, P, _ = pose_proj_fwd(pose, K, None, 1, rotation_mode, [1.0])
+        P = P[0]
+        warped = inverse_warp_fwd_P(img, depth, P, Kinv, padding_mode)
+        ctx.save_for_backward(img, depth, pose, K, Kinv, P)
+        ctx.cfg = (rotation_mode, padding_mode)
+        return warped
+
+    @staticmethod
+    def backward(ctx, gout):
+        img, depth, pose, K, Kinv, P = ctx.saved_tensors
+        rotation_mode, padding_mode = ctx.cfg
+        gimg, gdepth, gP = inverse_warp_bwd_P(gout, img, depth, P, Kinv, padding_mode, need_gimg=ctx.needs_input_grad[0])
+        gpose = None
+        if ctx.needs_input_grad[2]:
+            gpose = pose_proj_bwd(gP.unsqueeze(0), None, pose, K, 1, rotation_mode, [1.0])
+        return gimg, (gdepth if ctx.needs_input_grad[1] else None), gpose, None, None, None, None
+
+
+def pixel2cam(depth, intrinsics_inv):
+    """pixel2cam (inverse_warp.py:26-40), forward only."""
+    lib = _lib.load()
+    depth, Kinv = _req(depth, "depth", 3), _req(intrinsics_inv, "intrinsics_inv", 3)
+    if torch.is_grad_enabled() and (depth.requires_grad or Kinv.requires_grad):
+        raise DvfError("stand-alone pixel2cam is forward-only; differentiate through inverse_warp instead")
+    B, H, W = depth.shape
+    cam = torch.empty(B, 3, H, W, device=depth.device, dtype=torch.float32)
+    _lib.check(lib.dvf_pixel2cam(_ptr(depth), _ptr(Kinv), B, H, W, _ptr(cam), _stream()), "dvf_pixel2cam")
+    return cam
+
+
+def cam2pixel(cam_coords, proj_c2p_rot, proj_c2p_tr, padding_mode):
+    """cam2pixel (inverse_warp.py:43-74), forward only."""
+    lib = _lib.load()
+    cam = _req(cam_coords, "cam_coords", 4)
+    rot = None if proj_c2p_rot is None else _req(proj_c2p_rot, "proj_c2p_rot", 3)
+    tr = None if proj_c2p_tr is None else _req(proj_c2p_tr, "proj_c2p_tr").reshape(cam.shape[0], 3).contiguous()
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (cam_coords, proj_c2p_rot, proj_c2p_tr)):
+        raise DvfError("stand-alone cam2pixel is forward-only; differentiate through inverse_warp instead")
+    B, _, H, W = cam.shape
+    grid = torch.empty(B, H, W, 2, device=cam.device, dtype=torch.float32)
+    _lib.check(lib.dvf_cam2pixel(_ptr(cam), _ptr(rot), _ptr(tr), B, H, W, PADDING[padding_mode], _ptr(grid), _stream()),
+               "dvf_cam2pixel")
+    return grid
+
+
+# ------------------------------------------------------------------------------------------------
+# area pyramid
+# ------------------------------------------------------------------------------------------------
+def area_downsample(img, size):
+    """F.interpolate(img, size, mode='area') (loss_functions_sfm.py:18-19), no autograd."""
+    lib = _lib.load()
+    img = _req(img, "img", 4)
+    B, Cc, H, W = img.shape
+    h, w = int(size[0]), int(size[1])
+    if (h, w) == (H, W):
+        return img
+    out = torch.empty(B, Cc, h, w, device=img.device, dtype=torch.float32)
+    _lib.check(lib.dvf_area_downsample(_ptr(img), B * Cc, H, W, h, w, _ptr(out), _stream()), "dvf_area_downsample")
+    return out
+
+
+def area_pyramid(img, sizes: Sequence[Sequence[int]]):
+    """All requested levels of the 'area' pyramid of img; a single pass when they are /2,/4,/8."""
+    lib = _lib.load()
+    img = _req(img, "img", 4)
+    if img.requires_grad and torch.is_grad_enabled() and any(tuple(s) != tuple(img.shape[2:]) for s in sizes):
+        raise DvfError("area down-sampling of a tensor that requires grad is not implemented "
+                       "(the reference only down-samples input images)")
+    B, Cc, H, W = img.shape
+    sizes = [(int(s[0]), int(s[1])) for s in sizes]
+    small = [s for s in sizes if s != (H, W)]
+    uniq = sorted(set(small), reverse=True)
+    fast = (len(uniq) > 0 and uniq == [(H >> (k + 1), W >> (k + 1)) for k in range(len(uniq))]
+            and H % (1 << len(uniq)) == 0 and W % (1 << len(uniq)) == 0 and len(uniq) <= 3)
+    made = {(H, W): img}
+    if fast:
+        outs = [torch.empty(B, Cc, s[0], s[1], device=img.device, dtype=torch.float32) for s in uniq]
+        arr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        _lib.check(lib.dvf_area_pyramid(_ptr(img), B * Cc, H, W, len(outs), arr, _stream()), "dvf_area_pyramid")
+        made.update(dict(zip(uniq, outs)))
+    else:
+        for s in uniq:
+            made[s] = area_downsample(img, s)
+    return [made[s] for s in sizes]
+
+
+# ------------------------------------------------------------------------------------------------
+# fused reconstruction loss
+# ------------------------------------------------------------------------------------------------
+class _LossCfg:
+    __slots__ = ("V", "L", "rotation_mode", "padding_mode", "downscales", "has_expl", "expl_channels")
+
+
+def _scale_inplace(tensors: List[torch.Tensor], g: torch.Tensor):
+    ts = [t for t in tensors if t is not None]
+    if not ts:
+        return
+    try:
+        torch._foreach_mul_(ts, g)
+    except Exception:  # older foreach signatures
+        for t in ts:
+            t.mul_(g)
+
+
+class FusedPhotoLoss(torch.autograd.Function):
+    """sum over levels and views of mean|(tgt - warp(src_v)) * valid_v [* expl_v]| with every gradient
+    produced by the same single pass (dvf_photo_loss_fused); backward only scales by the upstream scalar.
+
+    inputs: cfg, pose [B,V,6], K, Kinv, then L target levels, L*V source levels (level-major),
+            L depth levels [B,h,w], and L explainability levels [B,>=V,h,w] if cfg.has_expl.
+    outputs: (loss scalar, terms [L*V] -- not differentiable, for logging)
+    """
+
+    @staticmethod
+    def forward(ctx, cfg, pose, K, Kinv, *tensors):
+        lib = _lib.load()
+        V, L = cfg.V, cfg.L
+        pose = _req(pose, "pose", 3)
+        K, Kinv = _req(K, "intrinsics", 3), _req(Kinv, "intrinsics_inv", 3)
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            raise DvfError("gradients w.r.t. the camera intrinsics are not implemented (unused by the reference)")
+        tgts = [_req(t, "tgt", 4) for t in tensors[0:L]]
+        srcs = [_req(t, "src", 4) for t in tensors[L:L + L * V]]
+        depths = [_req(t, "depth", 3) for t in tensors[L + L * V:2 * L + L * V]]
+        expls = [_req(t, "explainability_mask", 4) for t in tensors[2 * L + L * V:]] if cfg.has_expl else []
+        off = 4  # index of the first *tensors entry in needs_input_grad
+        need_tgt = [ctx.needs_input_grad[off + i] for i in range(L)]
+        need_src = [ctx.needs_input_grad[off + L + i] for i in range(L * V)]
+        need_depth = [ctx.needs_input_grad[off + L + L * V + i] for i in range(L)]
+        need_expl = [ctx.needs_input_grad[off + 2 * L + L * V + i] for i in range(L)] if cfg.has_expl else [False] * L
+        need_pose = ctx.needs_input_grad[1]
+
+        B, Cc = tgts[0].shape[0], tgts[0].shape[1]
+        dev = pose.device
+        vec = pose.reshape(B * V, 6)
+        _, P, Kinv_s = pose_proj_fwd(vec, K, Kinv, V, cfg.rotation_mode, cfg.downscales)
+        gP = torch.empty(L, B * V, 3, 4, device=dev, dtype=torch.float32) if need_pose else None
+        terms = torch.empty(L * V, device=dev, dtype=torch.float32)
+
+        levels = (dvf_level * L)()
+        grads = []  # order: tgt(L), src(L*V), depth(L), expl(L)
+        g_tgt, g_src, g_depth, g_expl = [None] * L, [None] * (L * V), [None] * L, [None] * L
+        for l in range(L):
+            lv = levels[l]
+            h, w = depths[l].shape[1], depths[l].shape[2]
+            if tgts[l].shape != (B, Cc, h, w):
+                raise AssertionError(f"level {l}: target {list(tgts[l].shape)} does not match depth {list(depths[l].shape)}")
+            lv.H, lv.W = h, w
+            lv.depth, lv.tgt = depths[l].data_ptr(), tgts[l].data_ptr()
+            lv.P, lv.Kinv = P[l].data_ptr(), Kinv_s[l].data_ptr()
+            for v in range(V):
+                s = srcs[l * V + v]
+                if s.shape != tgts[l].shape:
+                    raise AssertionError(f"level {l} view {v}: source {list(s.shape)} != target {list(tgts[l].shape)}")
+                lv.src[v] = s.data_ptr()
+                if need_src[l * V + v]:
+                    g_src[l * V + v] = torch.zeros_like(s)
+                    lv.gsrc[v] = g_src[l * V + v].data_ptr()
+            if cfg.has_expl:
+                e = expls[l]
+                if e.shape[0] != B or e.shape[1] < V or e.shape[2:] != (h, w):
+                    raise AssertionError(f"level {l}: explainability mask {list(e.shape)} does not match depth")
+                lv.expl, lv.expl_bstride = e.data_ptr(), e.shape[1] * h * w
+                if need_expl[l]:
+                    # dense [B,V,h,w]; channels >= V of a wider mask get zero gradient
+                    g_expl[l] = torch.empty(B, V, h, w, device=dev, dtype=torch.float32)
+                    lv.gexpl = g_expl[l].data_ptr()
+            if need_depth[l]:
+                g_depth[l] = torch.empty_like(depths[l])
+                lv.gdepth = g_depth[l].data_ptr()
+            if need_tgt[l]:
+                g_tgt[l] = torch.empty_like(tgts[l])
+                lv.gtgt = g_tgt[l].data_ptr()
+            if need_pose:
+                lv.gP = gP[l].data_ptr()
+        d = dvf_loss_desc(B, Cc, V, L, _lib.F32, _lib.NCHW, PADDING[cfg.padding_mode], 0)
+        nbytes = lib.dvf_photo_loss_workspace_bytes(C.byref(d), levels)
+        if nbytes == 0:
+            raise DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")
+        ws = workspace(nbytes, dev)
+        _lib.check(lib.dvf_photo_loss_fused(C.byref(d), levels, _ptr(terms), _ptr(ws), ws.numel(), _stream()),
+                   "dvf_photo_loss_fused")
+        g_pose = None
+        if need_pose:
+            g_pose = pose_proj_bwd(gP, None, vec, K, V, cfg.rotation_mode, cfg.downscales).reshape(B, V, 6)
+        for l in range(L):
+            if cfg.has_expl and need_expl[l] and expls[l].shape[1] > V:
+                full = torch.zeros_like(expls[l])
+                full[:, :V] = g_expl[l]
+                g_expl[l] = full
+        ctx.unit_grads = [g_pose] + g_tgt + g_src + g_depth + (g_expl if cfg.has_expl else [])
+        loss = terms.sum()
+        ctx.mark_non_differentiable(terms)
+        return loss, terms
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_terms):
+        grads = ctx.unit_grads
+        ctx.unit_grads = None
+        if grads is None:
+            raise RuntimeError("FusedPhotoLoss: backward called twice (gradients are produced by the forward pass)")
+        _scale_inplace(grads, g_loss)
+        return (None, grads[0], None, None) + tuple(grads[1:])
+
+
+def fused_photo_loss(tgt_levels, src_levels, depth_levels, pose, K, Kinv, expl_levels=None, downscales=None,
+                     rotation_mode="euler", padding_mode="zeros"):
+    """tgt_levels: L tensors [B,C,h,w]; src_levels: L lists of V tensors; depth_levels: L tensors [B,h,w];
+    pose [B,V,6]; expl_levels: None or L tensors [B,>=V,h,w].  Returns (loss, terms[L*V])."""
+    L = len(depth_levels)
+    V = pose.shape[1]
+    if V > _lib.DVF_MAX_VIEWS or L > _lib.DVF_MAX_LEVELS:
+        raise DvfError(f"at most {_lib.DVF_MAX_VIEWS} views and {_lib.DVF_MAX_LEVELS} levels per call")
+    cfg = _LossCfg()
+    cfg.V, cfg.L = V, L
+    cfg.rotation_mode, cfg.padding_mode = rotation_mode, padding_mode
+    cfg.downscales = [1.0] * L if downscales is None else [float(x) for x in downscales]
+    cfg.has_expl = expl_levels is not None
+    flat = list(tgt_levels) + [s for lvl in src_levels for s in lvl] + list(depth_levels)
+    if cfg.has_expl:
+        flat += list(expl_levels)
+    return FusedPhotoLoss.apply(cfg, pose, K, Kinv, *flat)

@@ -1,0 +1,117 @@
+"""Static-shape execution plan for the fused reconstruction loss: allocate once, launch many times.
+
+A training loop with fixed shapes binds its tensors once and then issues exactly three launches per
+step through the C ABI -- dvf_pose_proj_fwd, dvf_photo_loss_fused (all levels and views, forward +
+backward), dvf_pose_proj_bwd -- optionally captured into a CUDA graph so a step costs one graph
+launch.  No autograd bookkeeping, no allocation, no host synchronisation.  Gradients are those of
+`sum of loss terms` (upstream gradient 1), exactly what loss.backward() yields for the reference's
+photometric_reconstruction_loss (loss_functions_sfm.py:9-46 / loss_functions.py:7-20).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import PADDING, ROTATION, dvf_level, dvf_loss_desc
+
+
+class FusedLossPlan:
+    def __init__(self, tgt_levels: Sequence[torch.Tensor], src_levels: Sequence[Sequence[torch.Tensor]],
+                 depth_levels: Sequence[torch.Tensor], pose: torch.Tensor, K: torch.Tensor, Kinv: torch.Tensor,
+                 expl_levels: Optional[Sequence[torch.Tensor]] = None, downscales: Optional[Sequence[float]] = None,
+                 rotation_mode: str = "euler", padding_mode: str = "zeros", need_grad: bool = True):
+        self.lib = _lib.load()
+        dev = pose.device
+        L, V = len(depth_levels), pose.shape[1]
+        B, Cc = tgt_levels[0].shape[0], tgt_levels[0].shape[1]
+        self.B, self.C, self.V, self.L = B, Cc, V, L
+        self.rotation = ROTATION[rotation_mode]
+        self.inputs = (list(tgt_levels), [list(s) for s in src_levels], list(depth_levels), pose, K, Kinv,
+                       None if expl_levels is None else list(expl_levels))   # keep alive
+        for t in list(tgt_levels) + [s for lv in src_levels for s in lv] + list(depth_levels) + [pose, K, Kinv]:
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        ds = [1.0] * L if downscales is None else [float(x) for x in downscales]
+        self.ds = (C.c_float * L)(*ds)
+        self.P = torch.empty(L, B * V, 3, 4, device=dev)
+        self.Kinv_s = torch.empty(L, B, 3, 3, device=dev)
+        self.terms = torch.empty(L * V, device=dev)
+        self.gP = torch.empty(L, B * V, 3, 4, device=dev) if need_grad else None
+        self.gpose = torch.empty(B, V, 6, device=dev) if need_grad else None
+        self.gdepth = [torch.empty_like(d) for d in depth_levels] if need_grad else None
+        self.gexpl = ([torch.empty(B, V, e.shape[2], e.shape[3], device=dev) for e in expl_levels]
+                      if (need_grad and expl_levels is not None) else None)
+        self.levels = (dvf_level * L)()
+        for l in range(L):
+            lv = self.levels[l]
+            lv.H, lv.W = depth_levels[l].shape[1], depth_levels[l].shape[2]
+            lv.depth, lv.tgt = depth_levels[l].data_ptr(), tgt_levels[l].data_ptr()
+            for v in range(V):
+                lv.src[v] = src_levels[l][v].data_ptr()
+            lv.P, lv.Kinv = self.P[l].data_ptr(), self.Kinv_s[l].data_ptr()
+            if expl_levels is not None:
+                e = expl_levels[l]
+                lv.expl, lv.expl_bstride = e.data_ptr(), e.shape[1] * e.shape[2] * e.shape[3]
+            if need_grad:
+                lv.gdepth, lv.gP = self.gdepth[l].data_ptr(), self.gP[l].data_ptr()
+                if self.gexpl is not None:
+                    lv.gexpl = self.gexpl[l].data_ptr()
+        self.desc = dvf_loss_desc(B, Cc, V, L, _lib.F32, _lib.NCHW, PADDING[padding_mode], 0)
+        n = self.lib.dvf_photo_loss_workspace_bytes(C.byref(self.desc), self.levels)
+        if n == 0:
+            raise _lib.DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")
+        self.ws = torch.zeros(n, dtype=torch.uint8, device=dev)   # private workspace: plans may be in flight together
+        self.warped_px = sum(B * V * d.shape[1] * d.shape[2] for d in depth_levels)
+        self.n_launches = 3 if need_grad else 2
+        self.need_grad = need_grad
+
+    # -- the three launches ---------------------------------------------------------------------
+    def launch_pose_fwd(self, stream: int):
+        pose, K, Kinv = self.inputs[3], self.inputs[4], self.inputs[5]
+        _lib.check(self.lib.dvf_pose_proj_fwd(pose.data_ptr(), K.data_ptr(), Kinv.data_ptr(), self.B, self.V, self.rotation,
+                                              self.ds, self.L, None, self.P.data_ptr(), self.Kinv_s.data_ptr(), stream),
+                   "dvf_pose_proj_fwd")
+
+    def launch_loss(self, stream: int):
+        _lib.check(self.lib.dvf_photo_loss_fused(C.byref(self.desc), self.levels, self.terms.data_ptr(), self.ws.data_ptr(),
+                                                 self.ws.numel(), stream), "dvf_photo_loss_fused")
+
+    def launch_pose_bwd(self, stream: int):
+        pose, K = self.inputs[3], self.inputs[4]
+        _lib.check(self.lib.dvf_pose_proj_bwd(self.gP.data_ptr(), None, pose.data_ptr(), K.data_ptr(), self.B, self.V,
+                                              self.rotation, self.ds, self.L, self.gpose.data_ptr(), stream),
+                   "dvf_pose_proj_bwd")
+
+    def launch(self, stream: Optional[int] = None):
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        self.launch_pose_fwd(st)
+        self.launch_loss(st)
+        if self.need_grad:
+            self.launch_pose_bwd(st)
+
+    def capture(self, loss_only: bool = False) -> torch.cuda.CUDAGraph:
+        """Capture one step (or only the fused loss kernel) into a CUDA graph."""
+        self.launch()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            if loss_only:
+                self.launch_loss(torch.cuda.current_stream().cuda_stream)
+            else:
+                self.launch()
+        return g
+
+    def loss(self) -> torch.Tensor:
+        return self.terms.sum()
+
+    # -- algorithmic (compulsory) HBM bytes of one fused-loss launch, SURVEY 8(d) ------------------
+    def algorithmic_bytes(self) -> int:
+        e = 4
+        per_tpx = 4 + self.C * e + (4 if self.need_grad else 0)          # depth + target (+ d depth), once per target pixel
+        per_wpx = self.C * e                                              # source texels, once per warped pixel
+        if self.inputs[6] is not None:
+            per_wpx += 4 + (4 if self.need_grad else 0)                   # explainability read (+ its gradient)
+        tpx = self.warped_px // self.V
+        return tpx * per_tpx + self.warped_px * per_wpx

@@ -1,0 +1,44 @@
+"""Drop-in for pytorch_version/loss_functions.py of Depth-VO-Feat (used by unsupervise.py:28).
+
+photometric_reconstruction_loss runs as ONE fused CUDA launch (csrc/dvf_loss.cu) that warps both
+source views, applies the value-based validity masks and produces the loss together with its
+gradients; smooth_loss keeps the reference formula.  CUDA tensors only.
+"""
+from __future__ import division
+
+import torch
+
+from dvf_b200 import ops as _ops
+from inverse_warp import inverse_warp as _inverse_warp_checked
+
+
+def photometric_reconstruction_loss(img_R2, img_R1, img_L2, depth, T_2to1, T_R2L, intrinsics, intrinsics_inv,
+                                    rotation_mode='euler', padding_mode='zeros'):
+    """loss_functions.py:7-20: mean|(R2 - warp(R1; T_2to1)) * valid| + mean|(R2 - warp(L2; T_R2L)) * valid|.
+    Works for images (C=3) and for feature maps (any C, gradients flow to all three maps)."""
+    pose = torch.stack((T_2to1, T_R2L), dim=1)  # [B,2,6]
+    loss, _ = _ops.fused_photo_loss([img_R2], [[img_R1, img_L2]], [depth], pose, intrinsics, intrinsics_inv,
+                                    rotation_mode=rotation_mode, padding_mode=padding_mode)
+    return loss
+
+
+def smooth_loss(pred_map, scale_factor=1):
+    """loss_functions.py:23-41: second-order smoothness, sum over scales with weight /= scale_factor."""
+    maps = pred_map if type(pred_map) in (tuple, list) else [pred_map]
+    total, weight = 0, 1.
+    for m in maps:
+        dx = m[:, :, :, 1:] - m[:, :, :, :-1]
+        dy = m[:, :, 1:] - m[:, :, :-1]
+        dxx = dx[:, :, :, 1:] - dx[:, :, :, :-1]
+        dxy = dx[:, :, 1:] - dx[:, :, :-1]
+        dyx = dy[:, :, :, 1:] - dy[:, :, :, :-1]
+        dyy = dy[:, :, 1:] - dy[:, :, :-1]
+        total += (dxx.abs().mean() + dxy.abs().mean() + dyx.abs().mean() + dyy.abs().mean()) * weight
+        weight /= scale_factor
+    return total
+
+
+def inverse_warp(img, depth, pose, intrinsics, intrinsics_inv, rotation_mode='euler', padding_mode='zeros'):
+    """The copy embedded in loss_functions.py:198-231 has the 'B3HW' check disabled (:211)."""
+    return _inverse_warp_checked(img, depth, pose, intrinsics, intrinsics_inv, rotation_mode, padding_mode,
+                                 check_channels=False)

@@ -1,0 +1,179 @@
+/*
+ * dvf_b200.h -- C ABI of libdvf_b200.so: the B200 (sm_100a) implementation of
+ * Depth-VO-Feat's differentiable inverse warp and masked reconstruction losses.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one function of the
+ * reference's pytorch_version/ package (cited per entry as file:line, relative
+ * to the reference checkout) and is what a binding in the reference's own
+ * language (Python: ctypes) calls; see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no C++/torch types.
+ *  - All pointers are DEVICE pointers owned by the caller (torch tensors'
+ *    data_ptr()).  Nothing is allocated, nothing is synchronised; every launch
+ *    goes to the cudaStream_t the caller passes (as void*).
+ *  - Entries are re-entrant; there is no global state.  Scratch memory is a
+ *    caller-provided workspace whose size dvf_*_workspace_bytes() reports.  A
+ *    workspace must be zero-filled before its FIRST use (e.g. torch.zeros); the
+ *    kernels restore the words that must stay zero, so it can be reused by
+ *    later calls on the same stream without clearing.  One workspace per
+ *    in-flight call.
+ *  - Return value: 0 = DVF_OK, <0 = argument error (dvf_status), >0 =
+ *    cudaError_t of the failed launch.  dvf_strerror() names either.
+ *  - Geometry (depth, poses, intrinsics, P, gradients w.r.t. them) is fp32.
+ *    Images / feature maps are fp32 or bf16, NCHW or NHWC (dvf_desc).
+ *  - Arithmetic profile: the coordinate chain reproduces torch-CPU fp32
+ *    rounding step by step (FMA placement, true divisions), so bilinear cells
+ *    and validity masks are bit-identical to the reference run on the CPU.
+ */
+#ifndef DVF_B200_H_
+#define DVF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVF_ABI_VERSION 1
+#define DVF_MAX_VIEWS 4   /* source views per target in one loss call          */
+#define DVF_MAX_LEVELS 6  /* pyramid levels fused into one loss launch         */
+
+typedef enum dvf_status {
+  DVF_OK = 0,
+  DVF_EINVAL_SHAPE = -1,   /* a size is <= 0 or exceeds a DVF_MAX_* limit      */
+  DVF_EINVAL_DTYPE = -2,   /* unknown element type / layout / mode value       */
+  DVF_EINVAL_ALIGN = -3,   /* pointer not aligned for the element type         */
+  DVF_EINVAL_NULL = -4,    /* a required pointer is NULL                       */
+  DVF_EUNSUPPORTED = -5,   /* valid request this build does not implement      */
+  DVF_EWORKSPACE = -6      /* workspace missing or too small                   */
+} dvf_status;
+
+typedef enum dvf_dtype { DVF_F32 = 0, DVF_BF16 = 1 } dvf_dtype;
+typedef enum dvf_layout { DVF_NCHW = 0, DVF_NHWC = 1 } dvf_layout;
+typedef enum dvf_padding { DVF_PAD_ZEROS = 0, DVF_PAD_BORDER = 1 } dvf_padding;   /* inverse_warp.py:67, train.py:194 */
+typedef enum dvf_rotation { DVF_ROT_EULER = 0, DVF_ROT_QUAT = 1 } dvf_rotation;  /* inverse_warp.py:152-155 */
+
+/* Image-tensor descriptor shared by the warp and loss entries. */
+typedef struct dvf_desc {
+  int32_t B, C, H, W;
+  int32_t dtype;    /* dvf_dtype of img / warped / gout / gimg / tgt / src    */
+  int32_t layout;   /* dvf_layout of those tensors                            */
+  int32_t padding;  /* dvf_padding                                            */
+  int32_t reserved;
+} dvf_desc;
+
+int dvf_version(void);
+const char* dvf_strerror(int status);
+
+/* ---- pose_vec2mat / projection ------------------------------------------
+ * Replaces pose_vec2mat (inverse_warp.py:141-157, euler2mat :77-114, quat2mat
+ * :117-138), `intrinsics @ pose_mat` (inverse_warp.py:188) and the per-scale
+ * intrinsics of loss_functions_sfm.py:20-21.
+ *   vec        [n_pose,6]  (tx,ty,tz,rx,ry,rz); n_pose = B*V, b-major
+ *   K, Kinv    [B,3,3] or NULL (then only posemat is produced)
+ *   downscale  host array [n_levels] (img_H / level_h), n_levels may be 0
+ *   posemat    [n_pose,3,4] out, nullable
+ *   P          [n_levels,n_pose,3,4] out:  (K rows 0-1 / downscale) @ posemat
+ *   Kinv_s     [n_levels,B,3,3] out: Kinv with columns 0-1 * downscale        */
+int dvf_pose_proj_fwd(const float* vec, const float* K, const float* Kinv,
+                      int32_t B, int32_t V, int32_t rotation,
+                      const float* downscale, int32_t n_levels, float* posemat,
+                      float* P, float* Kinv_s, void* stream);
+
+/* Backward of the above w.r.t. vec (sums over levels), fp64 inside.
+ *   gP [n_levels,n_pose,3,4] (nullable), gposemat [n_pose,3,4] (nullable)
+ *   gvec [n_pose,6] out, written.                                            */
+int dvf_pose_proj_bwd(const float* gP, const float* gposemat, const float* vec,
+                      const float* K, int32_t B, int32_t V, int32_t rotation,
+                      const float* downscale, int32_t n_levels, float* gvec,
+                      void* stream);
+
+/* ---- pixel2cam / cam2pixel (inverse_warp.py:26-40, :43-74) ---------------
+ * Exposed because the reference exposes them; inverse_warp below fuses both. */
+int dvf_pixel2cam(const float* depth, const float* Kinv, int32_t B, int32_t H,
+                  int32_t W, float* cam /*[B,3,H,W]*/, void* stream);
+int dvf_cam2pixel(const float* cam /*[B,3,H,W]*/, const float* rot /*[B,3,3] dense, nullable*/,
+                  const float* tr /*[B,3] dense, nullable*/, int32_t B, int32_t H, int32_t W,
+                  int32_t padding, float* grid /*[B,H,W,2]*/, void* stream);
+
+/* ---- inverse_warp (inverse_warp.py:160-193) ------------------------------
+ * warped = grid_sample(img, cam2pixel(pixel2cam(depth,Kinv), P), padding),
+ * P = K @ pose_vec2mat(pose) [B,3,4].  valid (nullable, uint8 [B,H,W]) is the
+ * value-based mask of loss_functions.py:11: any_c(warped_c != 0).             */
+int dvf_inverse_warp_fwd(const dvf_desc* d, const void* img, const float* depth,
+                         const float* P, const float* Kinv, void* warped,
+                         uint8_t* valid, void* stream);
+
+size_t dvf_inverse_warp_bwd_workspace_bytes(const dvf_desc* d);
+
+/* gout = dL/dwarped.  gdepth [B,H,W] and gP [B,3,4] are written; gimg
+ * (nullable, same dtype/layout as img, fp32 only) is ACCUMULATED into and must
+ * be zero-filled by the caller.                                              */
+int dvf_inverse_warp_bwd(const dvf_desc* d, const void* gout, const void* img,
+                         const float* depth, const float* P, const float* Kinv,
+                         float* gdepth, float* gP, void* gimg, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---- fused masked reconstruction loss, forward + backward in one pass ----
+ * Replaces photometric_reconstruction_loss of loss_functions.py:7-20 (V=2,
+ * one level, images or feature maps), loss_functions_sfm.py:9-46 (V refs, n
+ * levels, explainability masks) and loss_function_sfm_old.py:7-46.
+ * For every level l and view v:
+ *   warped = inverse_warp(src[v], depth, P[:,v]);  valid = any_c(warped != 0)
+ *   terms[l*V+v] = mean_{B,C,H,W} | (tgt - warped) * valid [* expl[:,v]] |
+ * and, for upstream d(sum of terms) = 1, the gradients w.r.t. depth (summed
+ * over views), P, expl, src and tgt.  Any gradient pointer may be NULL.      */
+typedef struct dvf_level {
+  int32_t H, W;
+  const float* depth;               /* [B,H,W]                                */
+  const void* tgt;                  /* [B,C,H,W] or [B,H,W,C]                 */
+  const void* src[DVF_MAX_VIEWS];   /* like tgt                               */
+  const float* expl;                /* NULL or base of channel 0: element (b,v,y,x) at expl[b*expl_bstride + v*H*W + y*W + x] */
+  int64_t expl_bstride;
+  const float* P;                   /* [B,V,3,4]                              */
+  const float* Kinv;                /* [B,3,3]                                */
+  float* gdepth;                    /* [B,H,W] written                        */
+  float* gexpl;                     /* [B,V,H,W] dense, written               */
+  void* gsrc[DVF_MAX_VIEWS];        /* fp32, layout of src; ACCUMULATED       */
+  void* gtgt;                       /* fp32, layout of tgt; written           */
+  float* gP;                        /* [B,V,3,4] written                      */
+} dvf_level;
+
+typedef struct dvf_loss_desc {
+  int32_t B, C, V, n_levels;
+  int32_t dtype, layout, padding;
+  int32_t reserved;
+} dvf_loss_desc;
+
+size_t dvf_photo_loss_workspace_bytes(const dvf_loss_desc* d, const dvf_level* levels);
+
+/* terms: device float [n_levels*V], written (deterministic reduction order). */
+int dvf_photo_loss_fused(const dvf_loss_desc* d, const dvf_level* levels,
+                         float* terms, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---- neighbours of the path ----------------------------
+ * F.interpolate(img,(h,w),mode='area') for the integer factors 2,4,8
+ * (loss_functions_sfm.py:18-19): one pass over img writes all levels.        */
+int dvf_area_pyramid(const float* img /*[BC,H,W]*/, int32_t BC, int32_t H, int32_t W,
+                     int32_t n_out, float* const* outs /*host array of n_out device ptrs: /2,/4,/8*/,
+                     void* stream);
+
+/* Same operator for one arbitrary output size (h,w) -- adaptive average pooling windows
+ * [floor(o*I/O), ceil((o+1)*I/O)), as F.interpolate(mode='area') uses.               */
+int dvf_area_downsample(const float* img /*[BC,H,W]*/, int32_t BC, int32_t H, int32_t W,
+                        int32_t h, int32_t w, float* out /*[BC,h,w]*/, void* stream);
+
+/* ---- diagnostics -----------------------------------------------------------
+ * Compares the shared-reciprocal IEEE division of the coordinate chain with
+ * __fdiv_rn on n pseudo-random operand pairs (mode 0: float divisors, mode 1:
+ * integer divisors with a host-style reciprocal).  *mismatches: device u64,
+ * zeroed by the caller, receives the number of differing quotients.           */
+int dvf_selftest_fast_div(uint64_t seed, uint64_t n, int32_t mode, unsigned long long* mismatches, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVF_B200_H_ */

@@ -1,0 +1,148 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference (read-only checkout at
+/root/reference/pytorch_version) on torch-CPU fp32.  Runs only in the build container -- the GPU
+box has no reference checkout -- so the vectors are committed together with this script.
+
+    python oracle/gen_golden.py            # rewrites tests/golden/
+
+Each fixture holds the inputs, the reference's intermediate projection matrix P = K @ pose_mat
+(so the per-pixel path can be checked bit-for-bit independently of sin/cos implementations) and
+the reference's outputs and autograd gradients.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("DVF_REFERENCE", "/root/reference/pytorch_version")
+OUT = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, os.path.join(REPO, "depth-vo-feat_b200"))
+from dvf_b200 import synthetic as syn  # noqa: E402  (pure-torch input generator, no CUDA needed)
+
+
+def _ref_modules():
+    # the package dir of this repo has same-named drop-in modules: make sure the reference wins here
+    sys.path = [p for p in sys.path if not p.endswith("depth-vo-feat_b200")]
+    sys.path.insert(0, REF)
+    for name in ("inverse_warp", "loss_functions", "loss_functions_sfm", "loss_function_sfm_old"):
+        sys.modules.pop(name, None)
+    mods = {n: importlib.import_module(n) for n in ("inverse_warp", "loss_functions", "loss_functions_sfm",
+                                                     "loss_function_sfm_old")}
+    for m in mods.values():
+        assert os.path.realpath(m.__file__).startswith(os.path.realpath(REF)), m.__file__
+    return mods
+
+
+def _np(t):
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def _reset(mods):
+    for m in mods.values():
+        if hasattr(m, "pixel_coords"):
+            m.pixel_coords = None
+
+
+def case_inverse_warp(mods, name, B, C, H, W, kind, rot, pad, seed, smooth=True, feature=False):
+    iw = mods["loss_functions"] if C != 3 else mods["inverse_warp"]   # the copy in loss_functions accepts any C
+    d = syn.stereo_temporal_batch(B, H, W, seed=seed, C=C, smooth=smooth, temporal=kind if kind != "stereo" else "kitti",
+                                  feature=feature)
+    pose = d["T_R2L"] if kind == "stereo" else d["T_2to1"]
+    img = d["img_R1"].clone().requires_grad_(True)
+    depth = d["depth"].clone().requires_grad_(True)
+    pose_t = pose.clone().requires_grad_(True)
+    K, Kinv = d["intrinsics"], d["intrinsics_inv"]
+    _reset(mods)
+    warped = iw.inverse_warp(img, depth, pose_t, K, Kinv, rot, pad)
+    gout = torch.randn(warped.shape, generator=torch.Generator().manual_seed(seed + 100))
+    warped.backward(gout)
+    posemat = mods["inverse_warp"].pose_vec2mat(pose, rot)
+    P = K @ posemat
+    valid = (1 - (warped == 0).prod(1)).to(torch.uint8)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kind="inverse_warp", rotation_mode=rot, padding_mode=pad,
+                        img=_np(img), depth=_np(depth), pose=_np(pose), K=_np(K), Kinv=_np(Kinv), gout=_np(gout),
+                        posemat=_np(posemat), P=_np(P), warped=_np(warped), valid=_np(valid),
+                        gimg=_np(img.grad), gdepth=_np(depth.grad), gpose=_np(pose_t.grad))
+
+
+def case_loss_functions(mods, name, B, C, H, W, kind, seed, feature=False):
+    lf = mods["loss_functions"]
+    d = syn.stereo_temporal_batch(B, H, W, seed=seed, C=C, temporal=kind, feature=feature)
+    t = {k: v.clone() for k, v in d.items()}
+    req = ["depth", "T_2to1", "T_R2L"] + (["img_R2", "img_R1", "img_L2"] if feature else [])
+    for k in req:
+        t[k].requires_grad_(True)
+    _reset(mods)
+    loss = lf.photometric_reconstruction_loss(t["img_R2"], t["img_R1"], t["img_L2"], t["depth"], t["T_2to1"], t["T_R2L"],
+                                              t["intrinsics"], t["intrinsics_inv"])
+    loss.backward()
+    pv = mods["inverse_warp"].pose_vec2mat
+    P = torch.stack([d["intrinsics"] @ pv(d["T_2to1"]), d["intrinsics"] @ pv(d["T_R2L"])], 1)
+    out = dict(kind="loss_functions", loss=_np(loss), P=_np(P))
+    for k, v in d.items():
+        out[k] = _np(v)
+    for k in req:
+        out["g_" + k] = _np(t[k].grad)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+def case_sfm(mods, name, B, H, W, n_scales, seed, with_mask, rot, pad, old=False):
+    d = syn.stereo_temporal_batch(B, H, W, seed=seed)
+    depths = [syn.depth(B, H >> s, W >> s, seed + 10 + s).unsqueeze(1).requires_grad_(True) for s in range(n_scales)]
+    nch = 2
+    masks = [syn.explainability(B, nch, H >> s, W >> s, seed + 20 + s).requires_grad_(True) if with_mask else None
+             for s in range(n_scales)]
+    pose = torch.stack([d["T_2to1"], d["T_R2L"]], 1).clone().requires_grad_(True)
+    _reset(mods)
+    if old:
+        t1 = pose[:, 0]
+        loss = mods["loss_function_sfm_old"].photometric_reconstruction_loss(
+            d["img_R2"], d["img_R1"], d["img_L2"], depths, t1, pose[:, 1], masks, d["intrinsics"], d["intrinsics_inv"], rot, pad)
+    else:
+        loss = mods["loss_functions_sfm"].photometric_reconstruction_loss(
+            d["img_R2"], [d["img_R1"], d["img_L2"]], d["intrinsics"], d["intrinsics_inv"], depths, masks, pose, rot, pad)
+    loss.backward()
+    out = dict(kind="sfm_old" if old else "sfm", rotation_mode=rot, padding_mode=pad, n_scales=n_scales,
+               with_mask=with_mask, loss=_np(loss), pose=_np(pose), g_pose=_np(pose.grad))
+    for k in ("img_R2", "img_R1", "img_L2", "intrinsics", "intrinsics_inv"):
+        out[k] = _np(d[k])
+    pv = mods["inverse_warp"].pose_vec2mat
+    for s in range(n_scales):
+        out[f"depth{s}"] = _np(depths[s])
+        out[f"g_depth{s}"] = _np(depths[s].grad)
+        ds = H / (H >> s)
+        Ks = torch.cat((d["intrinsics"][:, 0:2] / ds, d["intrinsics"][:, 2:]), dim=1)
+        out[f"P{s}"] = _np(torch.stack([Ks @ pv(pose[:, v].detach(), rot) for v in range(2)], 1))
+        if with_mask:
+            out[f"mask{s}"] = _np(masks[s])
+            out[f"g_mask{s}"] = _np(masks[s].grad)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    torch.set_num_threads(1)
+    os.makedirs(OUT, exist_ok=True)
+    mods = _ref_modules()
+    case_inverse_warp(mods, "iw_large_euler_zeros", 2, 3, 16, 52, "large", "euler", "zeros", seed=1)
+    case_inverse_warp(mods, "iw_kitti_euler_zeros", 2, 3, 32, 104, "kitti", "euler", "zeros", seed=2)
+    case_inverse_warp(mods, "iw_stereo_euler_zeros", 2, 3, 32, 104, "stereo", "euler", "zeros", seed=3)
+    case_inverse_warp(mods, "iw_large_quat_border", 2, 3, 16, 52, "large", "quat", "border", seed=4)
+    case_inverse_warp(mods, "iw_tiny_noise_euler_zeros", 1, 3, 24, 80, "tiny", "euler", "zeros", seed=5, smooth=False)
+    case_inverse_warp(mods, "iw_feat8_kitti", 1, 8, 16, 52, "kitti", "euler", "zeros", seed=6, feature=True)
+    case_loss_functions(mods, "lf_images", 2, 3, 32, 104, "kitti", seed=7)
+    case_loss_functions(mods, "lf_features8", 2, 8, 16, 52, "kitti", seed=8, feature=True)
+    case_sfm(mods, "sfm_3scales_mask", 2, 32, 104, 3, seed=9, with_mask=True, rot="euler", pad="zeros")
+    case_sfm(mods, "sfm_2scales_nomask_quat_border", 2, 32, 104, 2, seed=10, with_mask=False, rot="quat", pad="border")
+    case_sfm(mods, "sfm_old_2scales_mask", 2, 32, 104, 2, seed=11, with_mask=True, rot="euler", pad="zeros", old=True)
+    tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
+    print("wrote", sorted(os.listdir(OUT)), f"{tot / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

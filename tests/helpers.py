@@ -1,0 +1,44 @@
+"""Shared helpers of the test-suite: golden fixtures, tolerance metrics, synthetic cases."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# Tolerances stated by BASELINE.json north_star: fp32 results within 1e-5 relative, masks bit-exact.
+RTOL_F32 = 1e-5
+
+
+def golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    return {k: (z[k].item() if z[k].ndim == 0 and z[k].dtype.kind in "US" else z[k]) for k in z.files}
+
+
+def golden_names(prefix):
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b|  (the survey's acceptance metric, Appendix B.5)."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    den = max(float(np.abs(b).max()), 1e-30)
+    return float(np.abs(a - b).max()) / den
+
+
+def assert_close(a, b, tol=RTOL_F32, what=""):
+    e = rel_err(a, b)
+    assert e <= tol, f"{what}: max-abs error / max|ref| = {e:.3e} > {tol:.1e}"
+
+
+def ulp_diff(a, b):
+    """largest distance in float32 ulps between two arrays (treats +0/-0 as equal)."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    ia = a.view(np.int32).astype(np.int64)
+    ib = b.view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia)
+    ib = np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
+    return int(np.abs(ia - ib).max()) if a.size else 0

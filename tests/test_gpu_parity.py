@@ -1,0 +1,377 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libdvf_b200.so) against the CPU oracle on the
+same seeded inputs, and against the golden vectors of the real reference.
+
+Tolerances (BASELINE.json north_star): fp32 warped images, loss and gradients within 1e-5 relative
+(max|a-b| / max|ref|); validity masks bit-exact.  Given the same projection matrix P the sampling
+positions are reproduced bit-for-bit, so warped images are compared for exact equality.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import RTOL_F32, assert_close, golden, golden_names, rel_err, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dvf_b200 import ops as _ops, _lib
+    _lib.load()
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def syn():
+    from dvf_b200 import synthetic
+    return synthetic
+
+
+# ------------------------------------------------------------------------------------------------
+def test_fast_division_matches_ieee(ops):
+    """the shared-reciprocal division used by the coordinate chain == __fdiv_rn on 2^30 operand pairs"""
+    from dvf_b200 import _lib
+    lib = _lib.load()
+    for mode in (0, 1):
+        bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+        _lib.check(lib.dvf_selftest_fast_div(1234 + mode, 1 << 30, mode, bad.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "selftest")
+        assert int(bad.item()) == 0, f"mode {mode}: {int(bad.item())} quotients differ from __fdiv_rn"
+
+
+@pytest.mark.parametrize("rot", ["euler", "quat"])
+@pytest.mark.parametrize("kind", ["kitti", "tiny", "large", "stereo"])
+def test_pose_proj_vs_oracle(ops, oracle, syn, rot, kind):
+    B, V = 16, 2
+    pose = syn.pose(B * V, kind, 3).numpy()
+    K, Kinv = syn.intrinsics(B, 128, 416)
+    ds = [1.0, 2.0, 4.0, 8.0]
+    pm, P, Ks = ops.pose_proj_fwd(cu(pose), K.cuda(), Kinv.cuda(), V, rot, ds, want_posemat=True)
+    opm = oracle.pose_vec2mat(pose, rot)
+    # CUDA sinf/cosf vs glibc: last-place differences allowed, nothing more
+    assert ulp_diff(npy(pm), opm) <= 2
+    for l, d in enumerate(ds):
+        oK, oKi = oracle.scale_intrinsics(K.numpy(), Kinv.numpy(), d)
+        assert np.array_equal(npy(Ks[l]), oKi)
+        # same posemat in => bit-identical P out
+        oP = oracle.project(np.repeat(oK, V, axis=0), npy(pm))
+        assert np.array_equal(npy(P[l]), oP)
+    # backward (fp64 analytic on both sides)
+    g = np.random.default_rng(0).standard_normal((len(ds), B * V, 3, 4)).astype(np.float32)
+    gv = ops.pose_proj_bwd(cu(g), None, cu(pose), K.cuda(), V, rot, ds)
+    ref = np.zeros((B * V, 6), np.float64)
+    for l, d in enumerate(ds):
+        oK, _ = oracle.scale_intrinsics(K.numpy(), Kinv.numpy(), d)
+        ref += oracle.pose_bwd(g[l], np.repeat(oK, V, axis=0), pose, rot)
+    assert_close(npy(gv), ref, what="gvec")
+
+
+CASES = [  # B, C, H, W, pose kind, smooth, padding
+    (4, 3, 128, 416, "kitti", True, "zeros"),
+    (4, 3, 128, 416, "stereo", True, "zeros"),
+    (2, 3, 128, 416, "tiny", False, "zeros"),
+    (3, 3, 16, 52, "large", True, "zeros"),
+    (2, 3, 64, 208, "kitti", True, "border"),
+    (2, 5, 33, 71, "large", True, "zeros"),     # ragged sizes, odd channel count
+    (1, 1, 7, 9, "kitti", True, "border"),
+    (1, 32, 32, 104, "kitti", True, "zeros"),   # feature-map shape
+]
+
+
+def _case(syn, B, C, H, W, kind, smooth, seed=21):
+    d = syn.stereo_temporal_batch(B, H, W, seed=seed, C=C, smooth=smooth, temporal=kind if kind != "stereo" else "kitti",
+                                  feature=C not in (1, 3))
+    pose = d["T_R2L"] if kind == "stereo" else d["T_2to1"]
+    return d, pose
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_inverse_warp_fwd_bwd_vs_oracle(ops, oracle, syn, case):
+    B, C, H, W, kind, smooth, pad = case
+    d, pose = _case(syn, B, C, H, W, kind, smooth)
+    K, Kinv = d["intrinsics"], d["intrinsics_inv"]
+    P = oracle.project(K.numpy(), oracle.pose_vec2mat(pose.numpy()))
+    img, depth = d["img_R1"].numpy(), d["depth"].numpy()
+    ow, ov = oracle.inverse_warp_P(img, depth, P, Kinv.numpy(), pad)
+    w, v = ops.inverse_warp_fwd_P(cu(img), cu(depth), cu(P), Kinv.cuda(), pad, want_valid=True)
+    assert np.array_equal(npy(v), ov), "validity mask must be bit-exact"
+    assert np.array_equal(npy(w), ow), "same P => bit-identical warped image"
+    gout = np.random.default_rng(1).standard_normal(img.shape).astype(np.float32)
+    ogi, ogd, ogP = oracle.inverse_warp_bwd_P(gout, img, depth, P, Kinv.numpy(), pad)
+    gi, gd, gP = ops.inverse_warp_bwd_P(cu(gout), cu(img), cu(depth), cu(P), Kinv.cuda(), pad)
+    assert_close(npy(gd), ogd, what="gdepth")
+    assert_close(npy(gi), ogi, what="gimg")
+    assert_close(npy(gP), ogP, what="gP")
+
+
+@pytest.mark.parametrize("V,with_expl,C,pad", [(1, False, 3, "zeros"), (2, False, 3, "zeros"), (2, True, 3, "zeros"),
+                                               (3, True, 3, "border"), (4, False, 3, "zeros"), (2, False, 8, "zeros"),
+                                               (2, True, 32, "zeros"), (1, True, 1, "zeros")])
+def test_fused_loss_single_level_vs_oracle(ops, oracle, syn, V, with_expl, C, pad):
+    B, H, W = 3, 48, 136
+    feat = C not in (1, 3)
+    imgs = syn.features(B, C, H, W, 5, n=V + 1) if feat else syn.images(B, C, H, W, 5, n=V + 1)
+    tgt, srcs = imgs[0], imgs[1:]
+    depth = syn.depth(B, H, W, 6)
+    kinds = ["kitti", "stereo", "large", "tiny"]
+    pose = torch.stack([syn.pose(B, kinds[v], 7 + v) for v in range(V)], 1)
+    K, Kinv = syn.intrinsics(B, H, W)
+    expl = syn.explainability(B, V, H, W, 9) if with_expl else None
+    Pn = np.stack([oracle.project(K.numpy(), oracle.pose_vec2mat(pose[:, v].numpy())) for v in range(V)], 1)
+    r = oracle.photo_loss_P(tgt.numpy(), [s.numpy() for s in srcs], depth.numpy(), Pn, Kinv.numpy(),
+                            expl=None if expl is None else expl.numpy(), padding_mode=pad, need_gsrc=True, need_gtgt=True)
+
+    t_tgt = tgt.cuda().requires_grad_(True)
+    t_srcs = [s.cuda().requires_grad_(True) for s in srcs]
+    t_depth = depth.cuda().requires_grad_(True)
+    t_pose = pose.cuda().requires_grad_(True)
+    t_expl = None if expl is None else expl.cuda().requires_grad_(True)
+    loss, terms = ops.fused_photo_loss([t_tgt], [t_srcs], [t_depth], t_pose, K.cuda(), Kinv.cuda(),
+                                       expl_levels=None if expl is None else [t_expl], padding_mode=pad)
+    loss.backward()
+    # P computed on the GPU may differ from the oracle's in the last place (sin/cos); when it does not,
+    # everything downstream is compared at 1e-5
+    _, P_gpu, _ = ops.pose_proj_fwd(t_pose.detach().reshape(B * V, 6), K.cuda(), None, V, "euler", [1.0])
+    same_P = np.array_equal(npy(P_gpu[0]).reshape(B, V, 3, 4), Pn)
+    tol = RTOL_F32 if same_P else 2e-3
+    assert_close(npy(terms), r["terms"], tol=RTOL_F32, what="loss terms")
+    assert abs(loss.item() - r["terms"].sum()) <= RTOL_F32 * r["terms"].sum()
+    assert_close(npy(t_depth.grad), r["gdepth"], tol=tol, what="gdepth")
+    assert_close(npy(t_tgt.grad), r["gtgt"], tol=tol, what="gtgt")
+    for v in range(V):
+        assert_close(npy(t_srcs[v].grad), r["gsrc"][v], tol=tol, what=f"gsrc{v}")
+        gp = oracle.pose_bwd(r["gP"][:, v], K.numpy(), pose[:, v].numpy())
+        assert_close(npy(t_pose.grad[:, v]), gp, tol=tol, what=f"gpose{v}")
+    if with_expl:
+        assert_close(npy(t_expl.grad), r["gexpl"], tol=tol, what="gexpl")
+
+
+def test_fused_loss_exact_P_path_vs_oracle(ops, oracle, syn):
+    """the C ABI takes P directly: with the oracle's P every output is held to 1e-5 and the
+    per-image dP reduction to the fp64 reference."""
+    import ctypes as C
+    from dvf_b200 import _lib
+    lib = _lib.load()
+    B, Cc, H, W, V = 4, 3, 128, 416, 2
+    d = syn.stereo_temporal_batch(B, H, W, seed=31)
+    K, Kinv = d["intrinsics"], d["intrinsics_inv"]
+    Pn = np.stack([oracle.project(K.numpy(), oracle.pose_vec2mat(d[k].numpy())) for k in ("T_2to1", "T_R2L")], 1)
+    r = oracle.photo_loss_P(d["img_R2"].numpy(), [d["img_R1"].numpy(), d["img_L2"].numpy()], d["depth"].numpy(), Pn,
+                            Kinv.numpy())
+    tgt, s0, s1, depth = d["img_R2"].cuda(), d["img_R1"].cuda(), d["img_L2"].cuda(), d["depth"].cuda()
+    P, Ki = cu(Pn), Kinv.cuda()
+    gdepth = torch.empty_like(depth)
+    gP = torch.empty(B, V, 3, 4, device="cuda")
+    terms = torch.empty(V, device="cuda")
+    lv = (_lib.dvf_level * 1)()
+    lv[0].H, lv[0].W = H, W
+    lv[0].depth, lv[0].tgt, lv[0].P, lv[0].Kinv = depth.data_ptr(), tgt.data_ptr(), P.data_ptr(), Ki.data_ptr()
+    lv[0].src[0], lv[0].src[1] = s0.data_ptr(), s1.data_ptr()
+    lv[0].gdepth, lv[0].gP = gdepth.data_ptr(), gP.data_ptr()
+    desc = _lib.dvf_loss_desc(B, Cc, V, 1, 0, 0, 0, 0)
+    n = lib.dvf_photo_loss_workspace_bytes(C.byref(desc), lv)
+    assert n > 0
+    ws = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for _ in range(3):   # reuse of the workspace + run-to-run determinism
+        _lib.check(lib.dvf_photo_loss_fused(C.byref(desc), lv, terms.data_ptr(), ws.data_ptr(), n, st), "loss")
+        outs.append((npy(terms).copy(), npy(gdepth).copy(), npy(gP).copy()))
+    for o in outs[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(o, outs[0])), "results must be bit-reproducible"
+    assert_close(outs[0][0], r["terms"], what="terms")
+    assert_close(outs[0][1], r["gdepth"], what="gdepth")
+    assert_close(outs[0][2], r["gP"], what="gP")
+    assert int((outs[0][1] != r["gdepth"]).sum()) == 0, "depth gradient follows the reference's fp32 sequence exactly"
+
+
+def test_fused_loss_multilevel_matches_per_level(ops, oracle, syn):
+    B, H, W, V, L = 2, 64, 208, 2, 4
+    d = syn.stereo_temporal_batch(B, H, W, seed=41)
+    K, Kinv = d["intrinsics"], d["intrinsics_inv"]
+    depths = [syn.depth(B, H >> s, W >> s, 50 + s) for s in range(L)]
+    expl = [syn.explainability(B, V, H >> s, W >> s, 60 + s) for s in range(L)]
+    pose = torch.stack([d["T_2to1"], d["T_R2L"]], 1)
+    sizes = [(H >> s, W >> s) for s in range(L)]
+    tg = ops.area_pyramid(d["img_R2"].cuda(), sizes)
+    r1 = ops.area_pyramid(d["img_R1"].cuda(), sizes)
+    l2 = ops.area_pyramid(d["img_L2"].cuda(), sizes)
+    for s in range(L):  # pyramid == torch-CPU 'area' interpolation, bit for bit
+        assert np.array_equal(npy(tg[s]), oracle.area_downsample(d["img_R2"].numpy(), *sizes[s]))
+    t_depths = [x.cuda().requires_grad_(True) for x in depths]
+    t_expl = [x.cuda().requires_grad_(True) for x in expl]
+    t_pose = pose.cuda().requires_grad_(True)
+    ds = [H / s[0] for s in sizes]
+    loss, terms = ops.fused_photo_loss(tg, [[r1[s], l2[s]] for s in range(L)], t_depths, t_pose, K.cuda(), Kinv.cuda(),
+                                       expl_levels=t_expl, downscales=ds)
+    loss.backward()
+    pm, P, Ks = ops.pose_proj_fwd(t_pose.detach().reshape(B * V, 6), K.cuda(), Kinv.cuda(), V, "euler", ds, want_posemat=True)
+    gpose = np.zeros((B, V, 6))
+    for s in range(L):
+        Pn = npy(P[s]).reshape(B, V, 3, 4)   # GPU P: per-pixel path compared exactly
+        oK, oKi = oracle.scale_intrinsics(K.numpy(), Kinv.numpy(), ds[s])
+        r = oracle.photo_loss_P(npy(tg[s]), [npy(r1[s]), npy(l2[s])], depths[s].numpy(), Pn, oKi, expl=expl[s].numpy())
+        assert_close(npy(terms[s * V:(s + 1) * V]), r["terms"], what=f"terms level {s}")
+        assert_close(npy(t_depths[s].grad), r["gdepth"], what=f"gdepth level {s}")
+        assert_close(npy(t_expl[s].grad), r["gexpl"], what=f"gexpl level {s}")
+        for v in range(V):
+            gpose[:, v] += oracle.pose_bwd(r["gP"][:, v], oK, pose[:, v].numpy())
+    assert_close(npy(t_pose.grad), gpose, what="gpose")
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors of the real reference, through the drop-in modules
+# ------------------------------------------------------------------------------------------------
+def _loose(same_P):
+    # identical P -> identical bilinear cells -> 1e-5; otherwise a last-place difference of cos() can
+    # move a handful of samples across a texel boundary (piece-wise constant position gradients)
+    return RTOL_F32 if same_P else 5e-3
+
+
+@pytest.mark.parametrize("name", golden_names("iw_"))
+def test_dropin_inverse_warp_golden(ops, name):
+    import inverse_warp as iw
+    g = golden(name)
+    rot, pad = g["rotation_mode"], g["padding_mode"]
+    img, depth, pose = cu(g["img"]).requires_grad_(True), cu(g["depth"]).requires_grad_(True), cu(g["pose"]).requires_grad_(True)
+    K, Kinv = cu(g["K"]), cu(g["Kinv"])
+    fn = iw.inverse_warp if g["img"].shape[1] == 3 else __import__("loss_functions").inverse_warp
+    warped = fn(img, depth, pose, K, Kinv, rot, pad)
+    pm = iw.pose_vec2mat(pose.detach(), rot)
+    assert ulp_diff(npy(pm), g["posemat"]) <= 2
+    _, P, _ = ops.pose_proj_fwd(pose.detach(), K, None, 1, rot, [1.0])
+    same_P = np.array_equal(npy(P[0]), g["P"])
+    warped.backward(cu(g["gout"]))
+    if same_P:
+        assert np.array_equal(npy(warped), g["warped"])
+        valid = (warped != 0).any(1).to(torch.uint8)
+        assert np.array_equal(npy(valid), g["valid"])
+    tol = _loose(same_P)
+    assert_close(npy(warped), g["warped"], tol=max(tol, 1e-5) if same_P else 2e-3, what="warped")
+    assert_close(npy(depth.grad), g["gdepth"], tol=tol, what="gdepth")
+    assert_close(npy(img.grad), g["gimg"], tol=tol, what="gimg")
+    assert_close(npy(pose.grad), g["gpose"], tol=tol, what="gpose")
+    # exact-P path: feed the reference's own P through the C ABI -> bit-identical forward, 1e-5 backward
+    w2, v2 = ops.inverse_warp_fwd_P(img.detach(), depth.detach(), cu(g["P"]), Kinv, pad, want_valid=True)
+    assert np.array_equal(npy(w2), g["warped"]) and np.array_equal(npy(v2), g["valid"])
+    gi, gd, gP = ops.inverse_warp_bwd_P(cu(g["gout"]), img.detach(), depth.detach(), cu(g["P"]), Kinv, pad)
+    assert_close(npy(gd), g["gdepth"], what="gdepth (reference P)")
+    assert_close(npy(gi), g["gimg"], what="gimg (reference P)")
+    gv = ops.pose_proj_bwd(gP.unsqueeze(0), None, pose.detach(), K, 1, rot, [1.0])
+    assert_close(npy(gv), g["gpose"], what="gpose (reference P)")
+
+
+@pytest.mark.parametrize("name", golden_names("lf_"))
+def test_dropin_loss_functions_golden(ops, name):
+    import loss_functions as lf
+    g = golden(name)
+    feat = "g_img_R1" in g
+    t = {k: cu(g[k]) for k in ("img_R2", "img_R1", "img_L2", "depth", "T_2to1", "T_R2L", "intrinsics", "intrinsics_inv")}
+    req = ["depth", "T_2to1", "T_R2L"] + (["img_R2", "img_R1", "img_L2"] if feat else [])
+    for k in req:
+        t[k].requires_grad_(True)
+    loss = lf.photometric_reconstruction_loss(t["img_R2"], t["img_R1"], t["img_L2"], t["depth"], t["T_2to1"], t["T_R2L"],
+                                              t["intrinsics"], t["intrinsics_inv"])
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= RTOL_F32 * abs(float(g["loss"]))
+    pose = torch.stack([t["T_2to1"], t["T_R2L"]], 1).detach()
+    B = pose.shape[0]
+    _, P, _ = ops.pose_proj_fwd(pose.reshape(B * 2, 6), t["intrinsics"], None, 2, "euler", [1.0])
+    tol = _loose(np.array_equal(npy(P[0]).reshape(B, 2, 3, 4), g["P"]))
+    for k in req:
+        assert_close(npy(t[k].grad), g["g_" + k], tol=tol, what="g_" + k)
+
+
+@pytest.mark.parametrize("name", golden_names("sfm_"))
+def test_dropin_sfm_golden(ops, name):
+    g = golden(name)
+    old = g["kind"] == "sfm_old"
+    rot, pad, n = g["rotation_mode"], g["padding_mode"], int(g["n_scales"])
+    with_mask = bool(g["with_mask"])
+    depths = [cu(g[f"depth{s}"]).requires_grad_(True) for s in range(n)]
+    masks = [cu(g[f"mask{s}"]).requires_grad_(True) if with_mask else None for s in range(n)]
+    pose = cu(g["pose"]).requires_grad_(True)
+    K, Kinv = cu(g["intrinsics"]), cu(g["intrinsics_inv"])
+    R2, R1, L2 = cu(g["img_R2"]), cu(g["img_R1"]), cu(g["img_L2"])
+    if old:
+        import loss_function_sfm as m
+        loss = m.photometric_reconstruction_loss(R2, R1, L2, depths, pose[:, 0], pose[:, 1], masks, K, Kinv, rot, pad)
+    else:
+        import loss_functions_sfm as m
+        loss = m.photometric_reconstruction_loss(R2, [R1, L2], K, Kinv, depths, masks, pose, rot, pad)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= RTOL_F32 * abs(float(g["loss"]))
+    B = pose.shape[0]
+    H = R2.shape[2]
+    ds = [H / depths[s].shape[2] for s in range(n)]
+    _, P, _ = ops.pose_proj_fwd(pose.detach().reshape(B * 2, 6), K, None, 2, rot, ds)
+    same_P = all(np.array_equal(npy(P[s]).reshape(B, 2, 3, 4), g[f"P{s}"]) for s in range(n))
+    tol = _loose(same_P)
+    for s in range(n):
+        assert_close(npy(depths[s].grad), g[f"g_depth{s}"], tol=tol, what=f"g_depth{s}")
+        if with_mask:
+            assert_close(npy(masks[s].grad), g[f"g_mask{s}"], tol=tol, what=f"g_mask{s}")
+    gp = npy(pose.grad) if pose.grad is not None else np.zeros_like(g["g_pose"])
+    assert_close(gp, g["g_pose"], tol=tol, what="g_pose")
+
+
+def test_full_size_properties(ops, syn):
+    """BASELINE config sizes (B=64, 128x416, 4 scales): size-independent properties instead of the oracle --
+    linearity of the loss in the mask weights, batch-sharding invariance, and gradient/loss consistency."""
+    B, H, W, L, V = 64, 128, 416, 4, 1
+    d = syn.stereo_temporal_batch(B, H, W, seed=71)
+    K, Kinv = d["intrinsics"].cuda(), d["intrinsics_inv"].cuda()
+    sizes = [(H >> s, W >> s) for s in range(L)]
+    ds = [float(1 << s) for s in range(L)]
+    tg = ops.area_pyramid(d["img_R2"].cuda(), sizes)
+    sr = ops.area_pyramid(d["img_L2"].cuda(), sizes)
+    depths = [syn.depth(B, h, w, 80 + i).cuda() for i, (h, w) in enumerate(sizes)]
+    pose = d["T_R2L"].cuda().unsqueeze(1)
+
+    def run(sl, expl=None):
+        dl = [x[sl].clone().requires_grad_(True) for x in depths]
+        p = pose[sl].clone().requires_grad_(True)
+        loss, terms = ops.fused_photo_loss([x[sl] for x in tg], [[x[sl]] for x in sr], dl, p, K[sl], Kinv[sl],
+                                           expl_levels=expl, downscales=ds)
+        loss.backward()
+        return loss.item(), terms.detach().cpu().numpy().astype(np.float64), [x.grad for x in dl], p.grad
+
+    full = slice(0, B)
+    loss, terms, gd, gp = run(full)
+    assert np.isfinite(loss) and loss > 0
+    # (1) mask linearity: a constant explainability weight c scales every term and gradient by c
+    c = 0.25
+    ex = [torch.full((B, 1, h, w), c, device="cuda") for (h, w) in sizes]
+    loss_c, terms_c, gd_c, gp_c = run(full, ex)
+    np.testing.assert_allclose(terms_c, c * terms, rtol=1e-6)
+    assert_close(gp_c.cpu().numpy(), c * gp.cpu().numpy(), what="pose grad linearity")
+    assert_close(gd_c[0].cpu().numpy(), c * gd[0].cpu().numpy(), what="depth grad linearity")
+    # (2) sharding the batch in two halves: terms average, gradients concatenate (scaled by the batch ratio)
+    la, ta, gda, gpa = run(slice(0, B // 2))
+    lb, tb, gdb, gpb = run(slice(B // 2, B))
+    np.testing.assert_allclose(0.5 * (ta + tb), terms, rtol=1e-6)
+    both = torch.cat([gda[0], gdb[0]]) * 0.5
+    assert torch.equal(both, gd[0]), "per-pixel depth gradients are independent of the batch split (up to the exact 1/2)"
+    assert_close(torch.cat([gpa, gpb]).cpu().numpy() * 0.5, gp.cpu().numpy(), what="pose grad sharding")
+    # (3) determinism
+    loss2, terms2, gd2, gp2 = run(full)
+    assert loss2 == loss and all(torch.equal(a, b) for a, b in zip(gd, gd2)) and torch.equal(gp, gp2)
+
+
+def test_errors_are_loud(ops, syn):
+    from dvf_b200 import DvfError
+    import inverse_warp as iw
+    d = syn.stereo_temporal_batch(1, 8, 12, seed=1)
+    with pytest.raises(DvfError):   # CPU tensors: no fallback
+        iw.inverse_warp(d["img_R1"], d["depth"], d["T_2to1"], d["intrinsics"], d["intrinsics_inv"])
+    with pytest.raises(AssertionError):   # reference's size check (inverse_warp.py:173)
+        iw.inverse_warp(d["img_R1"].cuda()[:, :2], d["depth"].cuda(), d["T_2to1"].cuda(), d["intrinsics"].cuda(),
+                        d["intrinsics_inv"].cuda())

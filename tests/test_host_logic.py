@@ -1,0 +1,108 @@
+"""CPU: host-side logic of the drop-in modules -- reference-compatible names, signatures, assertion
+behaviour, loud failure without CUDA tensors, and product/oracle separation."""
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(REPO, "depth-vo-feat_b200")
+
+
+def test_dropin_signatures_match_reference():
+    import inverse_warp as iw
+    import loss_function_sfm_old as old
+    import loss_functions as lf
+    import loss_functions_sfm as sfm
+
+    def params(f):
+        return [(p.name, p.default) for p in inspect.signature(f).parameters.values()]
+
+    E = inspect.Parameter.empty
+    # inverse_warp.py:160
+    assert params(iw.inverse_warp)[:7] == [("img", E), ("depth", E), ("pose", E), ("intrinsics", E), ("intrinsics_inv", E),
+                                           ("rotation_mode", "euler"), ("padding_mode", "zeros")]
+    assert params(iw.pose_vec2mat) == [("vec", E), ("rotation_mode", "euler")]                  # :141
+    assert [p[0] for p in params(iw.pixel2cam)] == ["depth", "intrinsics_inv"]                   # :26
+    assert [p[0] for p in params(iw.cam2pixel)] == ["cam_coords", "proj_c2p_rot", "proj_c2p_tr", "padding_mode"]  # :43
+    # loss_functions.py:7
+    assert params(lf.photometric_reconstruction_loss) == [
+        ("img_R2", E), ("img_R1", E), ("img_L2", E), ("depth", E), ("T_2to1", E), ("T_R2L", E), ("intrinsics", E),
+        ("intrinsics_inv", E), ("rotation_mode", "euler"), ("padding_mode", "zeros")]
+    assert params(lf.smooth_loss) == [("pred_map", E), ("scale_factor", 1)]
+    # loss_functions_sfm.py:9
+    assert params(sfm.photometric_reconstruction_loss) == [
+        ("tgt_img", E), ("ref_imgs", E), ("intrinsics", E), ("intrinsics_inv", E), ("depth", E),
+        ("explainability_mask", E), ("pose", E), ("rotation_mode", "euler"), ("padding_mode", "zeros")]
+    for name in ("explainability_loss", "smooth_loss", "compute_errors", "inverse_warp"):
+        assert hasattr(sfm, name)
+    # loss_function_sfm_old.py:7
+    assert params(old.photometric_reconstruction_loss) == [
+        ("img_R2", E), ("img_R1", E), ("img_L2", E), ("depth", E), ("T_2to1", E), ("T_R2L", E), ("mask", E),
+        ("intrinsics", E), ("intrinsics_inv", E), ("rotation_mode", "euler"), ("padding_mode", "zeros")]
+    import loss_function_sfm as alias   # the module unsupervise_sfm.py:29 imports
+    assert alias.photometric_reconstruction_loss is old.photometric_reconstruction_loss
+
+
+def test_check_sizes_assertion_text():
+    import inverse_warp as iw
+    with pytest.raises(AssertionError, match="wrong size for img, expected Bx3xHxW"):
+        iw.check_sizes(torch.zeros(2, 4, 5, 6), "img", "B3HW")
+    iw.check_sizes(torch.zeros(2, 3, 5, 6), "img", "B3HW")
+    with pytest.raises(AssertionError):
+        iw.check_sizes(torch.zeros(2, 5), "pose", "B6")
+
+
+def test_cpu_tensors_fail_loudly():
+    from dvf_b200 import DvfError
+    import inverse_warp as iw
+    import loss_functions as lf
+    B, H, W = 1, 8, 12
+    img, depth, pose = torch.rand(B, 3, H, W), torch.rand(B, H, W) + 1, torch.zeros(B, 6)
+    K = torch.eye(3).unsqueeze(0)
+    with pytest.raises(DvfError, match="no CPU fallback"):
+        iw.inverse_warp(img, depth, pose, K, K)
+    with pytest.raises(DvfError, match="no CPU fallback"):
+        lf.photometric_reconstruction_loss(img, img, img, depth, pose, pose, K, K)
+    with pytest.raises(DvfError):
+        iw.pose_vec2mat(pose)
+
+
+def test_smooth_and_explainability_helpers_on_cpu():
+    # these two are plain tensor algebra next to the CUDA path; check the formulas
+    import loss_functions as lf
+    import loss_functions_sfm as sfm
+    from oracle import cpu_oracle as O
+    g = torch.Generator().manual_seed(0)
+    maps = [torch.rand(2, 1, 16 >> s, 24 >> s, generator=g) + 0.5 for s in range(3)]
+    val = lf.smooth_loss(maps, 2.0)
+    ref, w = 0.0, 1.0
+    for m in maps:
+        ref += O.smooth_loss_one(m[:, 0].numpy()) * w
+        w /= 2.0
+    assert abs(float(val) - ref) < 1e-5 * ref
+    m = torch.rand(2, 2, 8, 8, generator=g) * 0.9 + 0.05
+    assert abs(float(sfm.explainability_loss([m])) - O.explainability_loss_one(m.numpy())) < 1e-6
+
+
+def test_product_never_imports_the_oracle():
+    pat = re.compile(r"^\s*(from|import)\s+oracle|cpu_oracle|libdvf_oracle|dvfo_", re.M)
+    for root, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not pat.search(src), f"{f} references the oracle"
+    for f in os.listdir(os.path.join(REPO, "include")):
+        assert not pat.search(open(os.path.join(REPO, "include", f)).read())
+
+
+def test_synthetic_inputs_are_deterministic():
+    from dvf_b200 import synthetic as syn
+    a = syn.stereo_temporal_batch(2, 16, 52, seed=3)
+    b = syn.stereo_temporal_batch(2, 16, 52, seed=3)
+    for k in a:
+        assert torch.equal(a[k], b[k])
+    assert a["depth"].min() > 3.0 and a["depth"].max() <= 50.0 + 1e-3
+    assert float(a["T_R2L"][0, 0]) == pytest.approx(0.53233)
