@@ -41,12 +41,16 @@ def _req(t, name, ndim=None):
     return t.contiguous()
 
 
-def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    """Zero-initialised scratch, one per (device, stream); the kernels keep it reusable."""
-    key = (device.index, _stream())
+def workspace(nbytes: int, device: torch.device, signature) -> torch.Tensor:
+    """Zero-initialised scratch, one per (device, stream, call signature).  The kernels restore the
+    ticket counters they use, so a workspace is reusable by later calls WITH THE SAME SHAPES; a call
+    with other shapes lays the counters out elsewhere and therefore gets its own buffer."""
+    key = (device.index, _stream(), signature)
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        if len(_WS) > 64:
+            _WS.clear()
+        ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
         _WS[key] = ws
     return ws
 
@@ -128,7 +132,7 @@ def inverse_warp_bwd_P(gout, img, depth, P, Kinv, padding_mode="zeros", need_gim
     gP = torch.empty(img.shape[0], 3, 4, device=img.device, dtype=torch.float32)
     gimg = torch.zeros_like(img) if need_gimg else None
     nbytes = lib.dvf_inverse_warp_bwd_workspace_bytes(C.byref(d))
-    ws = workspace(nbytes, img.device)
+    ws = workspace(nbytes, img.device, ('warp_bwd',) + tuple(img.shape))
     _lib.check(lib.dvf_inverse_warp_bwd(C.byref(d), _ptr(gout), _ptr(img), _ptr(depth), _ptr(P), _ptr(Kinv),
                                         _ptr(gdepth), _ptr(gP), _ptr(gimg), _ptr(ws), ws.numel(), _stream()),
                "dvf_inverse_warp_bwd")
@@ -323,7 +327,7 @@ class FusedPhotoLoss(torch.autograd.Function):
         nbytes = lib.dvf_photo_loss_workspace_bytes(C.byref(d), levels)
         if nbytes == 0:
             raise DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")
-        ws = workspace(nbytes, dev)
+        ws = workspace(nbytes, dev, ('loss', B, Cc, V, cfg.has_expl) + tuple(tuple(x.shape[1:]) for x in depths))
         _lib.check(lib.dvf_photo_loss_fused(C.byref(d), levels, _ptr(terms), _ptr(ws), ws.numel(), _stream()),
                    "dvf_photo_loss_fused")
         g_pose = None

@@ -15,9 +15,10 @@
  *  - Entries are re-entrant; there is no global state.  Scratch memory is a
  *    caller-provided workspace whose size dvf_*_workspace_bytes() reports.  A
  *    workspace must be zero-filled before its FIRST use (e.g. torch.zeros); the
- *    kernels restore the words that must stay zero, so it can be reused by
- *    later calls on the same stream without clearing.  One workspace per
- *    in-flight call.
+ *    kernels restore the ticket counters they use, so it can be reused without
+ *    clearing by later calls WITH THE SAME DESCRIPTOR (same shapes) on the same
+ *    stream.  Re-zero it (or use another one) when the shapes change.  One
+ *    workspace per in-flight call.
  *  - Return value: 0 = DVF_OK, <0 = argument error (dvf_status), >0 =
  *    cudaError_t of the failed launch.  dvf_strerror() names either.
  *  - Geometry (depth, poses, intrinsics, P, gradients w.r.t. them) is fp32.
