@@ -1,0 +1,24 @@
+// explicit instantiations of the fused loss kernels (split over files to build in parallel)
+#include "dvf_loss_kernel.cuh"
+
+namespace dvf {
+template <int kV, bool kZeros, bool kTma>
+static void launch_loss_c3_t(const LossParams& prm, int blocks, bool expl, bool grad, cudaStream_t st) {
+  if (expl) {
+    if (grad) photo_loss_c3x2_kernel<kV, kZeros, true, true, kTma><<<blocks, kLossThreads, 0, st>>>(prm);
+    else photo_loss_c3x2_kernel<kV, kZeros, true, false, kTma><<<blocks, kLossThreads, 0, st>>>(prm);
+  } else {
+    if (grad) photo_loss_c3x2_kernel<kV, kZeros, false, true, kTma><<<blocks, kLossThreads, 0, st>>>(prm);
+    else photo_loss_c3x2_kernel<kV, kZeros, false, false, kTma><<<blocks, kLossThreads, 0, st>>>(prm);
+  }
+}
+template <int kV, bool kZeros>
+void launch_loss_c3(const LossParams& prm, int blocks, bool expl, bool grad, bool tma, cudaStream_t st) {
+  if (tma) launch_loss_c3_t<kV, kZeros, true>(prm, blocks, expl, grad, st);
+  else launch_loss_c3_t<kV, kZeros, false>(prm, blocks, expl, grad, st);
+}
+template void launch_loss_c3<1, false>(const LossParams&, int, bool, bool, bool, cudaStream_t);
+template void launch_loss_c3<2, false>(const LossParams&, int, bool, bool, bool, cudaStream_t);
+template void launch_loss_c3<3, false>(const LossParams&, int, bool, bool, bool, cudaStream_t);
+template void launch_loss_c3<4, false>(const LossParams&, int, bool, bool, bool, cudaStream_t);
+}  // namespace dvf

@@ -1,0 +1,752 @@
+// dvf_loss_kernel.cuh -- device code of the fused masked reconstruction loss (forward + backward in
+// ONE pass over HBM).  See dvf_loss.cu for the host side and the reference citations.
+//
+// One launch covers every pyramid level and every source view of a loss call:
+//   * a CTA owns a contiguous run of target pixels of ONE image of ONE level, so the per-image
+//     projection P and K^-1 are CTA-uniform (kept in shared memory, broadcast reads);
+//   * each thread walks kPPT pixels per iteration with stride = CTA width => every depth / target
+//     load and every depth-gradient store is a fully coalesced 128 B line per warp; the loads of the
+//     NEXT iteration are issued before the current one is processed (software prefetch);
+//   * per pixel the depth / target values are read once and shared by all V views; the 4 bilinear
+//     taps per channel are read-only gathers (neighbouring lanes hit neighbouring texels; L1 absorbs
+//     the x0/x1 and y0/y1 reuse); the gathers of all kPPT pixels are issued back to back before any
+//     is consumed;
+//   * the hot path is branch-free straight-line code; pixels whose operands leave the range in which
+//     the shared-reciprocal divisions are exact (|q| > 2^100, NaN) are redone by a cold out-of-line
+//     routine using __fdiv_rn;
+//   * loss term and the 12 entries of dL/dP are accumulated per thread, folded with a 16-slot
+//     butterfly, then per CTA, and the LAST CTA of an image (atomic ticket) adds the CTA partials in
+//     a fixed order in fp64 -> deterministic, no output needs pre-zeroing, no second launch.
+#pragma once
+#include <type_traits>
+
+#include "dvf_internal.h"
+#include "dvf_math.cuh"
+#include "dvf_math2.cuh"
+#include "dvf_reduce.cuh"
+#include "dvf_tma.cuh"
+
+namespace dvf {
+
+constexpr int kLossThreads = 128;
+constexpr int kPPT = 2;  // pixels per thread per iteration (generic-C kernel; plan granularity)
+
+struct LevelDev {
+  int H, W, HW;
+  FastDiv divW;
+  Geo geo;
+  float inv_n;
+  int allow_fast;
+  const float* depth;
+  const float* tgt;
+  const float* src[DVF_MAX_VIEWS];
+  const float* expl;
+  long long expl_bstride;
+  const float* P;
+  const float* Kinv;
+  float* gdepth;
+  float* gexpl;
+  float* gsrc[DVF_MAX_VIEWS];
+  float* gtgt;
+  float* gP;
+  int block_begin, blocks_per_image, iters;
+  float* partials;        // [B*blocks_per_image][V][kRedSlots]
+  double* img_terms;      // [B][V]
+  unsigned* img_counter;  // [B]   zero between launches
+  unsigned* lvl_counter;  // [1]   zero between launches
+};
+
+struct LossParams {
+  int n_levels, B, C, V;
+  int need_grad, reserved;
+  float* terms;  // [n_levels*V]
+  LevelDev lv[DVF_MAX_LEVELS];
+};
+
+// ---- cold, out-of-line exact versions --------------------------------------------------------
+template <bool kZeros>
+__device__ __noinline__ Proj project_exact(const float* P /*smem*/, Cam c, const Geo* g) {
+  Proj o;
+  project<true, kZeros>(P, c, *g, o);
+  return o;
+}
+static __device__ __noinline__ ChainGrad chain_backward_exact(const float* P /*smem*/, Cam c, Proj p, Loc L, float gx, float gy,
+                                                              const Geo* g) {
+  ChainGrad o;
+  chain_backward<true>(P, c, p, L, gx, gy, *g, o);
+  return o;
+}
+
+// sign(d)/N with sign(0) = sign(NaN) = 0, gated by `gate`
+__device__ __forceinline__ float signed_unit(float d, float inv_n, bool gate) {
+  const bool nz = (d < 0.0f || d > 0.0f) && gate;
+  return nz ? copysignf(inv_n, d) : 0.0f;
+}
+
+// Shared tail of both kernels: CTA fold of acc[kV][16], partial write, ticket, image fold, level fold.
+template <int kV, int kThreadsT>
+__device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], const LossParams& prm, const LevelDev& lv,
+                                                  int l, int rel, int b, int C) {
+  __shared__ float s_red[kThreadsT / 32][kV][kRedSlots];
+  __shared__ int s_flag;
+  __shared__ double s_term[kThreadsT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int v = 0; v < kV; ++v) {
+    const float r = butterfly16(acc[v], lane);
+    if ((lane & 1) == 0) s_red[warp][v][butterfly_slot(lane)] = r;
+  }
+  __syncthreads();
+  float* my_part = lv.partials + (size_t)rel * kV * kRedSlots;
+  if (tid < kV * kRedSlots) {
+    const int v = tid / kRedSlots, s = tid % kRedSlots;
+    float t = 0.0f;
+#pragma unroll
+    for (int w8 = 0; w8 < kThreadsT / 32; ++w8) t += s_red[w8][v][s];
+    __stcg(my_part + tid, t);
+    __threadfence();   // only the writers need to publish
+  }
+  __syncthreads();
+  if (tid == 0) s_flag = (atomicAdd(lv.img_counter + b, 1u) == (unsigned)(lv.blocks_per_image - 1));
+  __syncthreads();
+  if (!s_flag) return;
+
+  // ---- last CTA of image b: fixed-order fp64 fold of the CTA partials ----------------
+  __threadfence();
+  const float* img_part = lv.partials + (size_t)b * lv.blocks_per_image * kV * kRedSlots;
+  for (int pair = tid >> 3; pair < kV * kRedSlots; pair += kThreadsT / 8) {
+    const int v = pair / kRedSlots, s = pair % kRedSlots;
+    const double sum = group8_sum(img_part + v * kRedSlots + s, lv.blocks_per_image, kV * kRedSlots, tid & 7);
+    if ((tid & 7) == 0) {
+      if (s < 12) {
+        if (lv.gP) lv.gP[((size_t)b * kV + v) * 12 + s] = (float)sum;
+      } else if (s == 12) {
+        lv.img_terms[(size_t)b * kV + v] = sum;
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    lv.img_counter[b] = 0u;
+    s_flag = (atomicAdd(lv.lvl_counter, 1u) == (unsigned)(prm.B - 1));
+  }
+  __syncthreads();
+  if (!s_flag) return;
+
+  // ---- last image of the level: loss terms ---------------------------------------------
+  __threadfence();
+  for (int v = 0; v < kV; ++v) {
+    double s = 0.0;
+    for (int bb = tid; bb < prm.B; bb += kThreadsT) s += __ldcg(lv.img_terms + (size_t)bb * kV + v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_term[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w8 = 0; w8 < kThreadsT / 32; ++w8) t += s_term[w8];
+      prm.terms[l * kV + v] = (float)(t / ((double)prm.B * (double)C * (double)lv.HW));
+    }
+    __syncthreads();
+  }
+  if (tid == 0) *lv.lvl_counter = 0u;
+}
+
+// ================================================================================================
+// C == 3 (images): everything of a pixel lives in registers.  No scatter / target-gradient outputs
+// here (requests for those go through the generic kernel below).
+//   kExpl  explainability weights present      kGrad  produce gradients (false: loss only)
+// One pixel per thread per iteration; latency is hidden by occupancy (>= 16 warps / SM), addresses
+// are per-image base pointers + 32-bit offsets.
+// ================================================================================================
+template <int kV, bool kZeros, bool kExpl, bool kGrad, int kMinBlocks = 4>
+__global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3_kernel(const __grid_constant__ LossParams prm) {
+  constexpr int kC = 3;
+  __shared__ __align__(16) float s_P[kV][12];
+  __shared__ __align__(16) float s_M[12];
+
+  int l = 0;
+  while (l + 1 < prm.n_levels && (int)blockIdx.x >= prm.lv[l + 1].block_begin) ++l;
+  const LevelDev& lv = prm.lv[l];
+  const int rel = (int)blockIdx.x - lv.block_begin;
+  const int b = rel / lv.blocks_per_image;
+  const int chunk = rel - b * lv.blocks_per_image;
+  const int tid = threadIdx.x;
+  const int H = lv.H, W = lv.W, HW = lv.HW;
+  const Geo geo = lv.geo;
+  const FastDiv divW = lv.divW;
+  const float inv_n = lv.inv_n;
+
+  if (tid < kV * 12) s_P[tid / 12][tid % 12] = lv.P[((size_t)b * kV + tid / 12) * 12 + tid % 12];
+  if (tid >= 64 && tid < 73) s_M[tid - 64] = lv.Kinv[b * 9 + (tid - 64)];
+  __syncthreads();
+
+  float acc[kV][kRedSlots];
+#pragma unroll
+  for (int v = 0; v < kV; ++v)
+#pragma unroll
+    for (int k = 0; k < kRedSlots; ++k) acc[v][k] = 0.0f;
+
+  // per-image base pointers; everything below indexes them with 32-bit offsets (3*HW < 2^31)
+  const float* const depth_b = lv.depth + (size_t)b * HW;
+  const float* const tgt0 = lv.tgt + (size_t)b * kC * HW;
+  const float* const tgt1 = tgt0 + HW;
+  const float* const tgt2 = tgt1 + HW;
+  float* const gdepth_b = lv.gdepth + (size_t)b * HW;   // only dereferenced when lv.gdepth != nullptr
+  const bool want_gdepth = lv.gdepth != nullptr;
+  const float* const expl_b = kExpl ? lv.expl + (size_t)b * lv.expl_bstride : nullptr;
+  float* const gexpl_b = (kExpl && lv.gexpl) ? lv.gexpl + (size_t)b * kV * HW : nullptr;
+  // the exact (cold) path is forced when the per-image matrices are not comfortably finite
+  bool mats_ok = lv.allow_fast != 0;
+  float M[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    M[k] = s_M[k];
+    mats_ok = mats_ok && (fabsf(M[k]) <= 1048576.0f /*2^20*/);
+  }
+#pragma unroll
+  for (int v = 0; v < kV; ++v)
+#pragma unroll
+    for (int k = 0; k < 12; ++k) mats_ok = mats_ok && (fabsf(s_P[v][k]) <= 1073741824.0f /*2^30*/);
+  // with |P| <= 2^30, |Kinv| <= 2^20, |depth| <= 2^30 and pixel indices < 2^15 every intermediate of the
+  // coordinate chain stays below 2^100 => the shared-reciprocal divisions are exact
+  const float depth_max = mats_ok ? 1073741824.0f : -1.0f;
+
+  const int px_end = min((chunk + 1) * (kLossThreads * lv.iters), HW);
+  for (int idx = chunk * (kLossThreads * lv.iters) + tid; idx < px_end; idx += kLossThreads) {
+    const float dep = ld_stream(depth_b + idx);
+    const float tg0 = ld_stream(tgt0 + idx), tg1 = ld_stream(tgt1 + idx), tg2 = ld_stream(tgt2 + idx);
+    Cam cam;
+    {
+      const int i = (int)fastdiv((uint32_t)idx, divW);
+      pixel_to_cam(M, dep, i, idx - i * W, cam);
+    }
+    const bool fast = fabsf(dep) <= depth_max;   // false for NaN
+    float gd = 0.0f;
+
+#pragma unroll
+    for (int v = 0; v < kV; ++v) {
+      float P[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) P[k] = s_P[v][k];
+      const float* const src0 = lv.src[v] + (size_t)b * kC * HW;
+
+      Proj pr;
+      Loc L;
+      project<false, kZeros>(P, cam, geo, pr);
+      if (__builtin_expect(!fast, 0)) pr = project_exact<kZeros>(&s_P[v][0], cam, &lv.geo);
+      locate<kZeros>(pr.xn, pr.yn, H, W, geo, L);
+
+      const int o0 = L.y0 * W + L.x0;          // nw tap, channel 0
+      const int o1 = o0 + HW, o2 = o1 + HW;
+      const float a00 = L.bnw ? __ldg(src0 + o0) : 0.0f, a01 = L.bne ? __ldg(src0 + o0 + 1) : 0.0f;
+      const float a10 = L.bsw ? __ldg(src0 + o0 + W) : 0.0f, a11 = L.bse ? __ldg(src0 + o0 + W + 1) : 0.0f;
+      const float b00 = L.bnw ? __ldg(src0 + o1) : 0.0f, b01 = L.bne ? __ldg(src0 + o1 + 1) : 0.0f;
+      const float b10 = L.bsw ? __ldg(src0 + o1 + W) : 0.0f, b11 = L.bse ? __ldg(src0 + o1 + W + 1) : 0.0f;
+      const float c00 = L.bnw ? __ldg(src0 + o2) : 0.0f, c01 = L.bne ? __ldg(src0 + o2 + 1) : 0.0f;
+      const float c10 = L.bsw ? __ldg(src0 + o2 + W) : 0.0f, c11 = L.bse ? __ldg(src0 + o2 + W + 1) : 0.0f;
+      float ex = 1.0f;
+      if (kExpl) ex = ld_stream(expl_b + v * HW + idx);
+
+      const float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
+      const float w0 = bilerp(a00, a01, a10, a11, wnw, wne, wsw, wse);
+      const float w1 = bilerp(b00, b01, b10, b11, wnw, wne, wsw, wse);
+      const float w2 = bilerp(c00, c01, c10, c11, wnw, wne, wsw, wse);
+      const bool any = (w0 != 0.0f) || (w1 != 0.0f) || (w2 != 0.0f);
+      const float e0 = sub(tg0, w0), e1 = sub(tg1, w1), e2 = sub(tg2, w2);            // tgt - warped
+      const float f0 = kExpl ? mul(e0, ex) : e0, f1 = kExpl ? mul(e1, ex) : e1, f2 = kExpl ? mul(e2, ex) : e2;
+      const float lsum = add(add(fabsf(f0), fabsf(f1)), fabsf(f2));
+      acc[v][12] += any ? lsum : 0.0f;
+      if (kGrad) {
+        const float s0 = signed_unit(f0, inv_n, any), s1 = signed_unit(f1, inv_n, any), s2 = signed_unit(f2, inv_n, any);
+        const float g0 = kExpl ? mul(s0, ex) : s0, g1 = kExpl ? mul(s1, ex) : s1, g2 = kExpl ? mul(s2, ex) : s2;
+        float gx = 0.0f, gy = 0.0f;
+        bilerp_grad(a00, a01, a10, a11, L, -g0, gx, gy);
+        bilerp_grad(b00, b01, b10, b11, L, -g1, gx, gy);
+        bilerp_grad(c00, c01, c10, c11, L, -g2, gx, gy);
+        if (kExpl) {
+          if (gexpl_b) st_stream(gexpl_b + v * HW + idx, add(add(mul(s0, e0), mul(s1, e1)), mul(s2, e2)));
+        }
+        ChainGrad cg;
+        chain_backward<false>(P, cam, pr, L, gx, gy, geo, cg);
+        if (__builtin_expect(!fast, 0)) cg = chain_backward_exact(&s_P[v][0], cam, pr, L, gx, gy, &lv.geo);
+        gd = add(gd, cg.gdepth);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) acc[v][r * 4 + k] = fmaf(cg.gq[r], cam.cam[k], acc[v][r * 4 + k]);
+          acc[v][r * 4 + 3] += cg.gq[r];
+        }
+      }
+    }  // views
+    if (kGrad && want_gdepth) st_stream(gdepth_b + idx, gd);
+  }  // pixels
+
+  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, rel, b, kC);
+}
+
+// ================================================================================================
+// C == 3, packed: each thread owns TWO horizontally adjacent target pixels and runs the whole
+// floating-point chain on (pixel A, pixel B) pairs with FFMA2 / FMUL2 / FADD2 (dvf_math2.cuh).
+// Same results bit for bit as the scalar kernel above; ~half the floating-point issue slots.
+//
+// kTma: the streaming inputs (depth, 3 target planes, explainability weights) of a CTA's run of pixels
+// are contiguous in memory; they are fetched by 1-D bulk asynchronous copies (TMA) into a kStages-deep
+// shared-memory ring, several chunks ahead of the computation, and the source rows around each chunk are
+// prefetched into L2.  This keeps tens of KB of HBM reads in flight per SM at zero register cost -- the
+// kernel is otherwise limited by how many loads its warps can have outstanding.  Requires HW % 4 == 0 and
+// 16-byte aligned tensors (checked on the host); otherwise the same kernel runs with plain loads.
+// ================================================================================================
+constexpr int kChunk = 2 * kLossThreads;   // pixels per chunk (one pair per thread)
+constexpr int kStages = 4;
+
+template <int kV, bool kZeros, bool kExpl, bool kGrad, bool kTma, int kMinBlocks = 4>
+__global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kernel(const __grid_constant__ LossParams prm) {
+  constexpr int kC = 3;
+  constexpr int kPlanes = 1 + kC + (kExpl ? kV : 0);   // streamed planes per chunk
+  __shared__ __align__(16) float s_P[kV][12];
+  __shared__ __align__(16) float s_M[12];
+  __shared__ __align__(128) float s_ring[kTma ? kStages : 1][kTma ? kPlanes : 1][kTma ? kChunk : 4];
+  __shared__ __align__(8) uint64_t s_full[kStages];
+
+  int l = 0;
+  while (l + 1 < prm.n_levels && (int)blockIdx.x >= prm.lv[l + 1].block_begin) ++l;
+  const LevelDev& lv = prm.lv[l];
+  const int rel = (int)blockIdx.x - lv.block_begin;
+  const int b = rel / lv.blocks_per_image;
+  const int chunk = rel - b * lv.blocks_per_image;
+  const int tid = threadIdx.x;
+  const int H = lv.H, W = lv.W, HW = lv.HW;
+  const Geo geo = lv.geo;
+  const Geo2 geo2 = make_geo2(geo);
+  const FastDiv divW = lv.divW;
+  const float inv_n = lv.inv_n;
+
+  if (tid < kV * 12) s_P[tid / 12][tid % 12] = lv.P[((size_t)b * kV + tid / 12) * 12 + tid % 12];
+  if (tid >= 64 && tid < 73) s_M[tid - 64] = lv.Kinv[b * 9 + (tid - 64)];
+  if (kTma && tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  f2 acc2[kV][12];     // dL/dP partial sums, (A,B) lanes folded at the end
+  float accl[kV];      // loss partial sums
+#pragma unroll
+  for (int v = 0; v < kV; ++v) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc2[v][k] = dup(0.0f);
+    accl[v] = 0.0f;
+  }
+
+  const float* const depth_b = lv.depth + (size_t)b * HW;
+  const float* const tgt0 = lv.tgt + (size_t)b * kC * HW;
+  float* const gdepth_b = lv.gdepth + (size_t)b * HW;
+  const bool want_gdepth = lv.gdepth != nullptr;
+  const float* const expl_b = kExpl ? lv.expl + (size_t)b * lv.expl_bstride : nullptr;
+  float* const gexpl_b = (kExpl && lv.gexpl) ? lv.gexpl + (size_t)b * kV * HW : nullptr;
+  bool mats_ok = lv.allow_fast != 0;
+  float M[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    M[k] = s_M[k];
+    mats_ok = mats_ok && (fabsf(M[k]) <= 1048576.0f);
+  }
+#pragma unroll
+  for (int v = 0; v < kV; ++v)
+#pragma unroll
+    for (int k = 0; k < 12; ++k) mats_ok = mats_ok && (fabsf(s_P[v][k]) <= 1073741824.0f);
+  const float depth_max = mats_ok ? 1073741824.0f : -1.0f;   // see photo_loss_c3_kernel
+
+  const float* src_b[kV];
+#pragma unroll
+  for (int v = 0; v < kV; ++v) src_b[v] = lv.src[v] + (size_t)b * kC * HW;
+
+  // this CTA owns pixels [px_begin, px_end) of image b, in chunks of kChunk (plan granularity 2*kLossThreads)
+  const int px_begin = chunk * (kChunk * lv.iters);
+  const int px_end = min(px_begin + kChunk * lv.iters, HW);
+  const int n_chunks = (px_end - px_begin + kChunk - 1) / kChunk;
+
+  // producer (thread 0): bulk copies of chunk k into ring stage k % kStages + L2 prefetch of the source rows
+  auto issue = [&](int k) {
+    const int start = px_begin + k * kChunk;
+    const uint32_t bytes = (uint32_t)(min(kChunk, px_end - start) * 4);   // multiple of 16 (HW % 4 == 0)
+    const int st = k % kStages;
+    mbar_expect_tx(&s_full[st], bytes * kPlanes);
+    bulk_g2s(&s_ring[st][0][0], depth_b + start, bytes, &s_full[st]);
+#pragma unroll
+    for (int c = 0; c < kC; ++c) bulk_g2s(&s_ring[st][1 + c][0], tgt0 + c * HW + start, bytes, &s_full[st]);
+    if (kExpl) {
+#pragma unroll
+      for (int v = 0; v < kV; ++v) bulk_g2s(&s_ring[st][1 + kC + v][0], expl_b + v * HW + start, bytes, &s_full[st]);
+    }
+    // the bilinear taps of these pixels lie in the same rows of the source image give or take the parallax:
+    // pull that band (+- 2 rows) towards L2 so that the gathers find it there
+    int lo = start - 2 * W, hi = start + kChunk + 2 * W;
+    lo = max(lo, 0) & ~3;
+    hi = min(hi, HW) & ~3;
+    if (hi > lo) {
+#pragma unroll
+      for (int v = 0; v < kV; ++v) {
+        const float* s0 = lv.src[v] + (size_t)b * kC * HW;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) bulk_prefetch_l2(s0 + c * HW + lo, (uint32_t)(hi - lo) * 4);
+      }
+    }
+  };
+  if (kTma && tid == 0) {
+    for (int k = 0; k < min(kStages, n_chunks); ++k) issue(k);
+  }
+
+  // one chunk; kTail = the chunk may contain lanes past the end of the run (only the last chunk can)
+  auto do_chunk = [&](int k, auto tail_tag) {
+    constexpr bool kTail = decltype(tail_tag)::value;
+    const int idxA = px_begin + k * kChunk + 2 * tid;
+    const int idxB = idxA + 1;
+    const bool liveA = !kTail || idxA < px_end, liveB = !kTail || idxB < px_end;
+    f2 dep, tg0, tg1, tg2;
+    f2 exv[kExpl ? kV : 1];
+    if (kTma) {
+      const int st = k % kStages;
+      mbar_wait(&s_full[st], (uint32_t)(k / kStages) & 1u);
+      dep = *reinterpret_cast<const f2*>(&s_ring[st][0][2 * tid]);
+      tg0 = *reinterpret_cast<const f2*>(&s_ring[st][1][2 * tid]);
+      tg1 = *reinterpret_cast<const f2*>(&s_ring[st][2][2 * tid]);
+      tg2 = *reinterpret_cast<const f2*>(&s_ring[st][3][2 * tid]);
+      if (kExpl) {
+#pragma unroll
+        for (int v = 0; v < kV; ++v) exv[v] = *reinterpret_cast<const f2*>(&s_ring[st][1 + kC + v][2 * tid]);
+      }
+    } else {
+      const int ia = kTail ? min(idxA, HW - 1) : idxA, ib = kTail ? min(idxB, HW - 1) : idxB;
+      dep = make_float2(ld_stream(depth_b + ia), ld_stream(depth_b + ib));
+      tg0 = make_float2(ld_stream(tgt0 + ia), ld_stream(tgt0 + ib));
+      tg1 = make_float2(ld_stream(tgt0 + HW + ia), ld_stream(tgt0 + HW + ib));
+      tg2 = make_float2(ld_stream(tgt0 + 2 * HW + ia), ld_stream(tgt0 + 2 * HW + ib));
+      if (kExpl) {
+#pragma unroll
+        for (int v = 0; v < kV; ++v) exv[v] = make_float2(ld_stream(expl_b + v * HW + ia), ld_stream(expl_b + v * HW + ib));
+      }
+    }
+    // dead lanes (past the end of the run) may read stale ring contents: give them a harmless depth; their
+    // taps are never loaded (all-zero => invalid => zero gradients) and nothing of theirs is stored
+    if (kTail) dep = make_float2(liveA ? dep.x : 1.0f, liveB ? dep.y : 1.0f);
+    Cam2 cam;
+    {
+      const int ca = kTail ? min(idxA, HW - 1) : idxA, cb = kTail ? min(idxB, HW - 1) : idxB;
+      const int iA = (int)fastdiv((uint32_t)ca, divW), jA = ca - iA * W;
+      const int iB = (int)fastdiv((uint32_t)cb, divW), jB = cb - iB * W;
+      pixel_to_cam2(M, dep, make_float2((float)iA, (float)iB), make_float2((float)jA, (float)jB), cam);
+    }
+    const bool fastA = fabsf(dep.x) <= depth_max, fastB = fabsf(dep.y) <= depth_max;   // false for NaN
+    const bool slow = !(fastA && fastB);
+    f2 gd = dup(0.0f);
+
+#pragma unroll
+    for (int v = 0; v < kV; ++v) {
+      float P[12];
+#pragma unroll
+      for (int q = 0; q < 12; ++q) P[q] = s_P[v][q];
+      const float* const src0 = src_b[v];
+
+      Proj2 pr;
+      Loc2 L;
+      project2<kZeros>(P, cam, geo2, pr);
+      if (__builtin_expect(slow, 0)) {   // redo the offending lane(s) with exact divisions
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h == 0 ? fastA : fastB) continue;
+          Cam c1;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            c1.ray[q] = h == 0 ? cam.ray[q].x : cam.ray[q].y;
+            c1.cam[q] = h == 0 ? cam.cam[q].x : cam.cam[q].y;
+          }
+          const Proj e = project_exact<kZeros>(&s_P[v][0], c1, &lv.geo);
+          if (h == 0) {
+            pr.qz.x = e.qz; pr.nZ.x = -e.Z; pr.u.x = e.u; pr.v.x = e.v; pr.xn.x = e.xn; pr.yn.x = e.yn; pr.mxA = e.mx; pr.myA = e.my;
+          } else {
+            pr.qz.y = e.qz; pr.nZ.y = -e.Z; pr.u.y = e.u; pr.v.y = e.v; pr.xn.y = e.xn; pr.yn.y = e.yn; pr.mxB = e.mx; pr.myB = e.my;
+          }
+        }
+      }
+      locate2<kZeros>(pr.xn, pr.yn, H, W, geo, geo2, L);
+
+      const int oA = L.y0A * W + L.x0A, oB = L.y0B * W + L.x0B;
+      const bool nwA = L.nwA && liveA, neA = L.neA && liveA, swA = L.swA && liveA, seA = L.seA && liveA;
+      const bool nwB = L.nwB && liveB, neB = L.neB && liveB, swB = L.swB && liveB, seB = L.seB && liveB;
+      f2 t00[kC], t01[kC], t10[kC], t11[kC];
+      {
+        const float* pa = ptr_off(src0, oA);
+        const float* pb = ptr_off(src0, oB);
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+          const float* pa1 = ptr_off(pa, W);
+          const float* pb1 = ptr_off(pb, W);
+          t00[c] = make_float2(nwA ? __ldg(pa) : 0.0f, nwB ? __ldg(pb) : 0.0f);
+          t01[c] = make_float2(neA ? __ldg(pa + 1) : 0.0f, neB ? __ldg(pb + 1) : 0.0f);
+          t10[c] = make_float2(swA ? __ldg(pa1) : 0.0f, swB ? __ldg(pb1) : 0.0f);
+          t11[c] = make_float2(seA ? __ldg(pa1 + 1) : 0.0f, seB ? __ldg(pb1 + 1) : 0.0f);
+          if (c + 1 < kC) {
+            pa = ptr_off(pa, HW);
+            pb = ptr_off(pb, HW);
+          }
+        }
+      }
+      const f2 ex = kExpl ? exv[kExpl ? v : 0] : dup(1.0f);
+
+      const f2 wnw = mul2(L.s, L.e), wne = mul2(L.s, L.w), wsw = mul2(L.n, L.e), wse = mul2(L.n, L.w);
+      f2 d0[kC], d1[kC];
+      const f2 w0 = bilerp2(t00[0], t01[0], t10[0], t11[0], wnw, wne, wsw, wse);
+      const f2 w1 = bilerp2(t00[1], t01[1], t10[1], t11[1], wnw, wne, wsw, wse);
+      const f2 w2 = bilerp2(t00[2], t01[2], t10[2], t11[2], wnw, wne, wsw, wse);
+      // dead lanes have all-zero taps => any = false
+      const bool anyA = (w0.x != 0.0f) || (w1.x != 0.0f) || (w2.x != 0.0f);
+      const bool anyB = (w0.y != 0.0f) || (w1.y != 0.0f) || (w2.y != 0.0f);
+      d0[0] = sub2(tg0, w0);
+      d0[1] = sub2(tg1, w1);
+      d0[2] = sub2(tg2, w2);
+#pragma unroll
+      for (int c = 0; c < kC; ++c) d1[c] = kExpl ? mul2(d0[c], ex) : d0[c];
+      const float lsA = add(add(fabsf(d1[0].x), fabsf(d1[1].x)), fabsf(d1[2].x));
+      const float lsB = add(add(fabsf(d1[0].y), fabsf(d1[1].y)), fabsf(d1[2].y));
+      accl[v] += (anyA ? lsA : 0.0f) + (anyB ? lsB : 0.0f);
+      if (kGrad) {
+        f2 gx = dup(0.0f), gy = dup(0.0f);
+        f2 su[kC];
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+          su[c] = make_float2(signed_unit(d1[c].x, inv_n, anyA), signed_unit(d1[c].y, inv_n, anyB));
+          const f2 g = kExpl ? mul2(su[c], ex) : su[c];
+          bilerp_grad2(t00[c], t01[c], t10[c], t11[c], L, neg2(g), gx, gy);
+        }
+        if (kExpl) {
+          if (gexpl_b) {
+            if (liveA)
+              st_stream(gexpl_b + v * HW + idxA, add(add(mul(su[0].x, d0[0].x), mul(su[1].x, d0[1].x)), mul(su[2].x, d0[2].x)));
+            if (liveB)
+              st_stream(gexpl_b + v * HW + idxB, add(add(mul(su[0].y, d0[0].y), mul(su[1].y, d0[1].y)), mul(su[2].y, d0[2].y)));
+          }
+        }
+        ChainGrad2 cg;
+        chain_backward2(P, cam, pr, L, gx, gy, geo2, cg);
+        if (__builtin_expect(slow, 0)) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 0 ? fastA : fastB) continue;
+            Cam c1;
+            Proj p1;
+            Loc L1;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              c1.ray[q] = h == 0 ? cam.ray[q].x : cam.ray[q].y;
+              c1.cam[q] = h == 0 ? cam.cam[q].x : cam.cam[q].y;
+            }
+            p1.qz = h == 0 ? pr.qz.x : pr.qz.y;
+            p1.Z = h == 0 ? -pr.nZ.x : -pr.nZ.y;
+            p1.rZ = 0.0f;
+            p1.u = h == 0 ? pr.u.x : pr.u.y;
+            p1.v = h == 0 ? pr.v.x : pr.v.y;
+            p1.xn = h == 0 ? pr.xn.x : pr.xn.y;
+            p1.yn = h == 0 ? pr.yn.x : pr.yn.y;
+            p1.mx = h == 0 ? pr.mxA : pr.mxB;
+            p1.my = h == 0 ? pr.myA : pr.myB;
+            L1.x0 = L1.y0 = 0;
+            L1.w = L1.e = L1.n = L1.s = 0.0f;
+            L1.bnw = L1.bne = L1.bsw = L1.bse = false;
+            L1.gmx = h == 0 ? L.gmx.x : L.gmx.y;
+            L1.gmy = h == 0 ? L.gmy.x : L.gmy.y;
+            const ChainGrad e = chain_backward_exact(&s_P[v][0], c1, p1, L1, h == 0 ? gx.x : gx.y, h == 0 ? gy.x : gy.y, &lv.geo);
+            if (h == 0) {
+              cg.gq[0].x = e.gq[0]; cg.gq[1].x = e.gq[1]; cg.gq[2].x = e.gq[2]; cg.gdepth.x = e.gdepth;
+            } else {
+              cg.gq[0].y = e.gq[0]; cg.gq[1].y = e.gq[1]; cg.gq[2].y = e.gq[2]; cg.gdepth.y = e.gdepth;
+            }
+          }
+        }
+        gd = make_float2(add(gd.x, cg.gdepth.x), add(gd.y, cg.gdepth.y));
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) acc2[v][r * 4 + q] = fma2(cg.gq[r], cam.cam[q], acc2[v][r * 4 + q]);
+          acc2[v][r * 4 + 3] = add2(acc2[v][r * 4 + 3], cg.gq[r]);
+        }
+      }
+    }  // views
+    if (kGrad && want_gdepth) {
+      float* const gp = ptr_off(gdepth_b, idxA);
+      if (liveA) st_stream(gp, gd.x);
+      if (liveB) st_stream(gp + 1, gd.y);
+    }
+    if (kTma) {
+      __syncthreads();   // every thread has consumed ring stage k % kStages
+      if (tid == 0 && k + kStages < n_chunks) issue(k + kStages);
+    }
+  };
+  for (int k = 0; k + 1 < n_chunks; ++k) do_chunk(k, std::false_type{});
+  if (n_chunks > 0) {
+    if (px_end - px_begin == n_chunks * kChunk) do_chunk(n_chunks - 1, std::false_type{});
+    else do_chunk(n_chunks - 1, std::true_type{});
+  }
+
+  float acc[kV][kRedSlots];
+#pragma unroll
+  for (int v = 0; v < kV; ++v) {
+#pragma unroll
+    for (int q = 0; q < 12; ++q) acc[v][q] = acc2[v][q].x + acc2[v][q].y;
+    acc[v][12] = accl[v];
+    acc[v][13] = acc[v][14] = acc[v][15] = 0.0f;
+  }
+  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, rel, b, kC);
+}
+
+// ================================================================================================
+// any channel count (feature maps in NCHW): channels are walked in a loop, twice when gradients
+// to the maps are requested (pass 1 decides the value-based mask, pass 2 scatters)
+// ================================================================================================
+template <int kV, bool kZeros>
+__global__ void __launch_bounds__(kLossThreads, 4) photo_loss_cn_kernel(const __grid_constant__ LossParams prm) {
+  __shared__ __align__(16) float s_P[kV][12];
+  __shared__ __align__(16) float s_M[12];
+
+  int l = 0;
+  while (l + 1 < prm.n_levels && (int)blockIdx.x >= prm.lv[l + 1].block_begin) ++l;
+  const LevelDev& lv = prm.lv[l];
+  const int rel = (int)blockIdx.x - lv.block_begin;
+  const int b = rel / lv.blocks_per_image;
+  const int chunk = rel - b * lv.blocks_per_image;
+  const int tid = threadIdx.x;
+  const int H = lv.H, W = lv.W, HW = lv.HW, C = prm.C;
+  const Geo geo = lv.geo;
+  const bool need_grad = prm.need_grad != 0;
+  const bool allow_fast = lv.allow_fast != 0;
+  const bool has_expl = lv.expl != nullptr;
+  const float inv_n = lv.inv_n;
+
+  if (tid < kV * 12) s_P[tid / 12][tid % 12] = lv.P[((size_t)b * kV + tid / 12) * 12 + tid % 12];
+  if (tid >= 64 && tid < 73) s_M[tid - 64] = lv.Kinv[b * 9 + (tid - 64)];
+  __syncthreads();
+
+  float acc[kV][kRedSlots];
+#pragma unroll
+  for (int v = 0; v < kV; ++v)
+#pragma unroll
+    for (int k = 0; k < kRedSlots; ++k) acc[v][k] = 0.0f;
+
+  const size_t img_off = (size_t)b * C * HW;
+  const float* depth_b = lv.depth + (size_t)b * HW;
+  const float* tgt_b = lv.tgt + img_off;
+  float* gtgt_b = lv.gtgt ? lv.gtgt + img_off : nullptr;
+  const int n_px = kLossThreads * kPPT * lv.iters;
+  const int px_begin = chunk * n_px + tid;
+
+  for (int q = 0; q < kPPT * lv.iters; ++q) {
+    const int idx = px_begin + q * kLossThreads;
+    const bool live = idx < HW;
+    Cam cam;
+    {
+      float M[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) M[k] = s_M[k];
+      const int i = (int)fastdiv((uint32_t)idx, lv.divW);
+      pixel_to_cam(M, live ? ld_stream(depth_b + idx) : 1.0f, i, idx - i * W, cam);
+    }
+    float gd = 0.0f;
+#pragma unroll
+    for (int v = 0; v < kV; ++v) {
+      float P[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) P[k] = s_P[v][k];
+      const float* src_b = lv.src[v] + img_off;
+      float* gsrc_b = lv.gsrc[v] ? lv.gsrc[v] + img_off : nullptr;
+      Proj pr;
+      Loc L;
+      const bool fast = project<false, kZeros>(P, cam, geo, pr) && allow_fast;
+      if (__builtin_expect(!fast, 0)) pr = project_exact<kZeros>(&s_P[v][0], cam, &lv.geo);
+      locate<kZeros>(pr.xn, pr.yn, H, W, geo, L);
+      const bool bnw = L.bnw && live, bne = L.bne && live, bsw = L.bsw && live, bse = L.bse && live;
+      const int o_nw = L.y0 * W + L.x0;
+      const float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
+      const float ex = (has_expl && live) ? ld_stream(lv.expl + (size_t)b * lv.expl_bstride + (size_t)v * HW + idx) : 1.0f;
+      float gx = 0.0f, gy = 0.0f, ge = 0.0f, lsum = 0.0f;
+      bool any = false;
+      // pass 1: mask, loss, d/d(ix,iy) assuming the pixel is valid
+#pragma unroll 2
+      for (int c = 0; c < C; ++c) {
+        const float* r0 = src_b + (size_t)c * HW + o_nw;
+        const float a0 = bnw ? __ldg(r0) : 0.0f, a1 = bne ? __ldg(r0 + 1) : 0.0f;
+        const float a2 = bsw ? __ldg(r0 + W) : 0.0f, a3 = bse ? __ldg(r0 + W + 1) : 0.0f;
+        const float t = live ? ld_stream(tgt_b + (size_t)c * HW + idx) : 0.0f;
+        const float wv = bilerp(a0, a1, a2, a3, wnw, wne, wsw, wse);
+        any |= (wv != 0.0f);
+        const float d0 = sub(t, wv);
+        const float d1 = has_expl ? mul(d0, ex) : d0;
+        lsum = add(lsum, fabsf(d1));
+        const float gd1 = signed_unit(d1, inv_n, true);
+        const float g = has_expl ? mul(gd1, ex) : gd1;
+        ge = add(ge, mul(gd1, d0));
+        bilerp_grad(a0, a1, a2, a3, L, -g, gx, gy);
+      }
+      if (!any) {
+        lsum = 0.0f;
+        ge = 0.0f;
+        gx = 0.0f;
+        gy = 0.0f;
+      }
+      acc[v][12] += lsum;
+      if (need_grad) {
+        // pass 2: gradients to the target map and scatter to the source map
+        if (live && (gsrc_b || gtgt_b)) {
+          for (int c = 0; c < C; ++c) {
+            float g = 0.0f;
+            if (any) {
+              const float* r0 = src_b + (size_t)c * HW + o_nw;
+              const float a0 = bnw ? __ldg(r0) : 0.0f, a1 = bne ? __ldg(r0 + 1) : 0.0f;
+              const float a2 = bsw ? __ldg(r0 + W) : 0.0f, a3 = bse ? __ldg(r0 + W + 1) : 0.0f;
+              const float wv = bilerp(a0, a1, a2, a3, wnw, wne, wsw, wse);
+              const float d0 = sub(ld_stream(tgt_b + (size_t)c * HW + idx), wv);
+              const float d1 = has_expl ? mul(d0, ex) : d0;
+              const float gd1 = signed_unit(d1, inv_n, true);
+              g = has_expl ? mul(gd1, ex) : gd1;
+            }
+            if (gtgt_b) {   // the same thread visits the views in order: plain read-modify-write
+              float* qg = gtgt_b + (size_t)c * HW + idx;
+              *qg = (v == 0) ? g : add(*qg, g);
+            }
+            if (gsrc_b && any) {
+              float* gp = gsrc_b + (size_t)c * HW + o_nw;
+              if (bnw) atomicAdd(gp, mul(wnw, -g));
+              if (bne) atomicAdd(gp + 1, mul(wne, -g));
+              if (bsw) atomicAdd(gp + W, mul(wsw, -g));
+              if (bse) atomicAdd(gp + W + 1, mul(wse, -g));
+            }
+          }
+        }
+        if (lv.gexpl && live) st_stream(lv.gexpl + ((size_t)b * kV + v) * HW + idx, ge);
+        ChainGrad cg;
+        chain_backward<false>(P, cam, pr, L, gx, gy, geo, cg);
+        if (__builtin_expect(!fast, 0)) cg = chain_backward_exact(&s_P[v][0], cam, pr, L, gx, gy, &lv.geo);
+        if (live) {
+          gd = add(gd, cg.gdepth);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) acc[v][r * 4 + k] = fmaf(cg.gq[r], cam.cam[k], acc[v][r * 4 + k]);
+            acc[v][r * 4 + 3] += cg.gq[r];
+          }
+        }
+      }
+    }
+    if (need_grad && live && lv.gdepth) st_stream(lv.gdepth + (size_t)b * HW + idx, gd);
+  }
+  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, rel, b, C);
+}
+
+template <int kV, bool kZeros>
+void launch_loss_c3(const LossParams& prm, int blocks, bool expl, bool grad, bool tma, cudaStream_t st);
+template <int kV, bool kZeros>
+void launch_loss_cn(const LossParams& prm, int blocks, cudaStream_t st);
+
+}  // namespace dvf

@@ -15,7 +15,7 @@ namespace dvf {
 struct WarpParams {
   int B, C, H, W, HW;
   FastDiv divW;
-  float fW1, fH1, rW1, rH1, halfW, halfH;
+  Geo geo;
   int allow_fast, zeros_padding;
   int blocks_per_image;
   const float* img;
@@ -36,6 +36,19 @@ struct WarpParams {
 
 constexpr int kWarpPPT = 2;
 
+// cold, out-of-line exact versions (operands outside the guarded range of the shared-reciprocal divisions)
+template <bool kZeros>
+__device__ __noinline__ Proj warp_project_exact(const float* P, Cam c, Geo g) {
+  Proj o;
+  project<true, kZeros>(P, c, g, o);
+  return o;
+}
+static __device__ __noinline__ ChainGrad warp_chain_backward_exact(const float* P, Cam c, Proj p, Loc L, float gx, float gy, Geo g) {
+  ChainGrad o;
+  chain_backward<true>(P, c, p, L, gx, gy, g, o);
+  return o;
+}
+
 __device__ __forceinline__ void load_PM(const WarpParams& p, int b, float (&P)[12], float (&M)[9]) {
 #pragma unroll
   for (int k = 0; k < 12; ++k) P[k] = __ldg(p.P + b * 12 + k);
@@ -43,6 +56,7 @@ __device__ __forceinline__ void load_PM(const WarpParams& p, int b, float (&P)[1
   for (int k = 0; k < 9; ++k) M[k] = __ldg(p.Kinv + b * 9 + k);
 }
 
+template <bool kZeros>
 __global__ void __launch_bounds__(kThreads) inverse_warp_fwd_kernel(const __grid_constant__ WarpParams p) {
   const int b = blockIdx.x / p.blocks_per_image;
   const int chunk = blockIdx.x - b * p.blocks_per_image;
@@ -51,7 +65,6 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_fwd_kernel(const __grid
   const int HW = p.HW, W = p.W, H = p.H;
   const float* img_b = p.img + (size_t)b * p.C * HW;
   float* out_b = p.warped + (size_t)b * p.C * HW;
-  const bool zeros = p.zeros_padding != 0;
 #pragma unroll
   for (int q = 0; q < kWarpPPT; ++q) {
     const int idx = chunk * (kThreads * kWarpPPT) + q * kThreads + threadIdx.x;
@@ -61,13 +74,9 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_fwd_kernel(const __grid
     Proj pr;
     Loc L;
     pixel_to_cam(M, ld_stream(p.depth + (size_t)b * HW + idx), i, j, cam);
-    if (zeros) {
-      project<true>(P, cam, p.fW1, p.fH1, p.rW1, p.rH1, p.allow_fast != 0, pr);
-      locate<true>(pr.xn, pr.yn, H, W, p.halfW, p.halfH, L);
-    } else {
-      project<false>(P, cam, p.fW1, p.fH1, p.rW1, p.rH1, p.allow_fast != 0, pr);
-      locate<false>(pr.xn, pr.yn, H, W, p.halfW, p.halfH, L);
-    }
+    const bool fast = project<false, kZeros>(P, cam, p.geo, pr) && (p.allow_fast != 0);
+    if (__builtin_expect(!fast, 0)) pr = warp_project_exact<kZeros>(p.P + b * 12, cam, p.geo);
+    locate<kZeros>(pr.xn, pr.yn, H, W, p.geo, L);
     const int o_nw = L.y0 * W + L.x0;
     const float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
     bool any = false;
@@ -83,6 +92,7 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_fwd_kernel(const __grid
   }
 }
 
+template <bool kZeros>
 __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_kernel(const __grid_constant__ WarpParams p) {
   __shared__ float s_red[kThreads / 32][kRedSlots];
   __shared__ int s_flag;
@@ -95,7 +105,6 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_kernel(const __grid
   const float* img_b = p.img + (size_t)b * p.C * HW;
   const float* gout_b = p.gout + (size_t)b * p.C * HW;
   float* gimg_b = p.gimg ? p.gimg + (size_t)b * p.C * HW : nullptr;
-  const bool zeros = p.zeros_padding != 0;
   float acc[kRedSlots];
 #pragma unroll
   for (int k = 0; k < kRedSlots; ++k) acc[k] = 0.0f;
@@ -109,13 +118,9 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_kernel(const __grid
     Proj pr;
     Loc L;
     pixel_to_cam(M, ld_stream(p.depth + (size_t)b * HW + idx), i, j, cam);
-    if (zeros) {
-      project<true>(P, cam, p.fW1, p.fH1, p.rW1, p.rH1, p.allow_fast != 0, pr);
-      locate<true>(pr.xn, pr.yn, H, W, p.halfW, p.halfH, L);
-    } else {
-      project<false>(P, cam, p.fW1, p.fH1, p.rW1, p.rH1, p.allow_fast != 0, pr);
-      locate<false>(pr.xn, pr.yn, H, W, p.halfW, p.halfH, L);
-    }
+    const bool fast = project<false, kZeros>(P, cam, p.geo, pr) && (p.allow_fast != 0);
+    if (__builtin_expect(!fast, 0)) pr = warp_project_exact<kZeros>(p.P + b * 12, cam, p.geo);
+    locate<kZeros>(pr.xn, pr.yn, H, W, p.geo, L);
     const int o_nw = L.y0 * W + L.x0;
     const float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
     float gx = 0.0f, gy = 0.0f;
@@ -134,7 +139,8 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_kernel(const __grid
       }
     }
     ChainGrad cg;
-    chain_backward(P, cam, pr, L, gx, gy, p.fW1, p.fH1, p.rW1, p.rH1, cg);
+    chain_backward<false>(P, cam, pr, L, gx, gy, p.geo, cg);
+    if (__builtin_expect(!fast, 0)) cg = warp_chain_backward_exact(p.P + b * 12, cam, pr, L, gx, gy, p.geo);
     st_stream(p.gdepth + (size_t)b * HW + idx, cg.gdepth);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -224,13 +230,8 @@ static int fill_params(const dvf_desc* d, WarpParams& p) {
   p.W = d->W;
   p.HW = d->H * d->W;
   p.divW = make_fastdiv((uint32_t)d->W);
-  p.fW1 = (float)(d->W - 1);
-  p.fH1 = (float)(d->H - 1);
+  p.geo = make_geo(d->H, d->W);
   p.allow_fast = d->W > 1 && d->H > 1;
-  p.rW1 = p.allow_fast ? (float)(1.0 / (double)p.fW1) : 0.0f;
-  p.rH1 = p.allow_fast ? (float)(1.0 / (double)p.fH1) : 0.0f;
-  p.halfW = (float)d->W / 2.0f;
-  p.halfH = (float)d->H / 2.0f;
   p.zeros_padding = d->padding == DVF_PAD_ZEROS;
   p.blocks_per_image = (p.HW + kThreads * kWarpPPT - 1) / (kThreads * kWarpPPT);
   return DVF_OK;
@@ -253,7 +254,10 @@ DVF_EXPORT int dvf_inverse_warp_fwd(const dvf_desc* d, const void* img, const fl
   p.Kinv = Kinv;
   p.warped = static_cast<float*>(warped);
   p.valid = valid;
-  inverse_warp_fwd_kernel<<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  if (p.zeros_padding)
+    inverse_warp_fwd_kernel<true><<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    inverse_warp_fwd_kernel<false><<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return launch_status();
 }
 
@@ -285,7 +289,10 @@ DVF_EXPORT int dvf_inverse_warp_bwd(const dvf_desc* d, const void* gout, const v
   p.partials = static_cast<float*>(workspace);
   p.img_counter = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) +
                                               align_up((size_t)p.blocks_per_image * p.B * kRedSlots * sizeof(float), 256));
-  inverse_warp_bwd_kernel<<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  if (p.zeros_padding)
+    inverse_warp_bwd_kernel<true><<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    inverse_warp_bwd_kernel<false><<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return launch_status();
 }
 
