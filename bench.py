@@ -300,7 +300,7 @@ def run_b200(args):
         traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get("photo_loss_kernel_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "dvf::photo_loss_kernel<3,1> (dvf_photo_loss_fused)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "dvf::photo_loss_c3x2_kernel<1,zeros,noexpl,grad,tma> (dvf_photo_loss_fused)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": bytes_launch, "bytes_per_warped_px": bytes_launch / wpx_step,

@@ -53,7 +53,7 @@ static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) 
   const long long want_blocks = 16ll * num_sms();
   int iters = (int)(total_px / (chunk * want_blocks));
   if (iters < 1) iters = 1;
-  if (iters > 16) iters = 16;
+  if (iters > 64) iters = 64;
   size_t off = 0;
   int begin = 0;
   for (int l = 0; l < d->n_levels; ++l) {
