@@ -9,8 +9,8 @@ warped px/s of the fused warp+loss fwd+bwd, and % of the HBM roofline).
 Workload (BASELINE.json configs[1], SURVEY 8d "C2"): 4-scale stereo photometric loss fwd+bwd, batch 64
 per GPU at 128x416 (levels 128x416, 64x208, 32x104, 16x52), one source view (the rectified-stereo pose),
 fp32 NCHW, synthetic KITTI-shaped inputs, image pyramids prebuilt (they are inputs of the path, 8d).
-A step = dvf_pose_proj_fwd + dvf_photo_loss_fused (all levels, loss + all gradients) + dvf_pose_proj_bwd,
-replayed from a CUDA graph.  Steps rotate over several distinct input sets whose total size exceeds L2.
+A step = ONE launch of dvf_photo_loss_fused_pose (pose_vec2mat + projection in the kernel prologue, warp + loss +
+all gradients over all levels, pose backward in the epilogue), replayed from a CUDA graph.  Steps rotate over several distinct input sets whose total size exceeds L2.
 Multi-GPU: batch sharded, B=64 per rank (weak scaling), no data-path collective; one NCCL all-reduce of the
 loss terms closes the timed region (logging exchange).
 """
@@ -300,7 +300,7 @@ def run_b200(args):
         traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get("photo_loss_kernel_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "dvf::photo_loss_c3x2_kernel<1,zeros,noexpl,grad,tma> (dvf_photo_loss_fused)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "dvf::photo_loss_c3x2_kernel<1,zeros,noexpl,grad,tma> (dvf_photo_loss_fused_pose)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": bytes_launch, "bytes_per_warped_px": bytes_launch / wpx_step,
@@ -361,7 +361,7 @@ def run_b200(args):
                        "depth_field": "iid-noise (stress)" if args.iid_depth else "smooth (17x17 box-filtered disparity)",
                        "pyramid": "prebuilt inputs (SURVEY 8d)", "parallelism": f"batch-sharded dp{world}",
                        "l2_policy": f"{args.sets} rotating input sets, {args.sets * set_bytes / 1e6:.0f} MB > 126 MB L2",
-                       "step": "CUDA-graph replay of pose_proj_fwd + photo_loss_fused + pose_proj_bwd"},
+                       "step": "CUDA-graph replay of ONE launch: dvf_photo_loss_fused_pose (pose_vec2mat+projection, warp+loss+all gradients over 4 levels, pose backward)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": plans[0].n_launches * args.steps,
             "warped_px_per_step_per_gpu": wpx_step,

@@ -21,6 +21,7 @@ struct Plan {
   int block_begin[DVF_MAX_LEVELS];
   int total_blocks;
   size_t off_partials[DVF_MAX_LEVELS], off_terms[DVF_MAX_LEVELS], off_cnt[DVF_MAX_LEVELS], off_lcnt[DVF_MAX_LEVELS];
+  size_t off_gM, off_pcnt;
   size_t bytes;
 };
 
@@ -74,6 +75,10 @@ static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) 
     pl.off_lcnt[l] = off;
     off += 256;
   }
+  pl.off_gM = off;
+  off += align_up((size_t)d->n_levels * d->B * d->V * 12 * sizeof(double), 256);
+  pl.off_pcnt = off;
+  off += align_up((size_t)d->B * sizeof(unsigned), 256);
   pl.total_blocks = begin;
   pl.bytes = off;
   return DVF_OK;
@@ -89,8 +94,8 @@ DVF_EXPORT size_t dvf_photo_loss_workspace_bytes(const dvf_loss_desc* d, const d
   return pl.bytes;
 }
 
-DVF_EXPORT int dvf_photo_loss_fused(const dvf_loss_desc* d, const dvf_level* levels, float* terms,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_pose_args* pose, float* terms,
+                    void* workspace, size_t workspace_bytes, void* stream) {
   Plan pl;
   int st = make_plan(d, levels, pl);
   if (st != DVF_OK) return st;
@@ -106,14 +111,27 @@ DVF_EXPORT int dvf_photo_loss_fused(const dvf_loss_desc* d, const dvf_level* lev
   prm.C = d->C;
   prm.V = d->V;
   const bool zeros = d->padding == DVF_PAD_ZEROS;
-  prm.reserved = 0;
+  prm.rotation = 0;
+  prm.pose_vec = nullptr;
+  prm.K = prm.Kinv = nullptr;
+  prm.gvec = nullptr;
+  if (pose) {
+    if (!pose->vec || !pose->K || !pose->Kinv || !pose->downscale) return DVF_EINVAL_NULL;
+    if (pose->rotation != DVF_ROT_EULER && pose->rotation != DVF_ROT_QUAT) return DVF_EINVAL_DTYPE;
+    prm.rotation = pose->rotation;
+    prm.pose_vec = pose->vec;
+    prm.K = pose->K;
+    prm.Kinv = pose->Kinv;
+    prm.gvec = pose->gvec;
+  }
   prm.terms = terms;
   bool need_grad = false;
   char* ws = static_cast<char*>(workspace);
   for (int l = 0; l < d->n_levels; ++l) {
     const dvf_level& s = levels[l];
     LevelDev& t = prm.lv[l];
-    if (!s.depth || !s.tgt || !s.P || !s.Kinv) return DVF_EINVAL_NULL;
+    if (!s.depth || !s.tgt) return DVF_EINVAL_NULL;
+    if (!pose && (!s.P || !s.Kinv)) return DVF_EINVAL_NULL;
     if (!aligned(s.depth, 4) || !aligned(s.tgt, 4) || !aligned(s.P, 4) || !aligned(s.Kinv, 4)) return DVF_EINVAL_ALIGN;
     t.H = s.H;
     t.W = s.W;
@@ -121,6 +139,7 @@ DVF_EXPORT int dvf_photo_loss_fused(const dvf_loss_desc* d, const dvf_level* lev
     t.divW = make_fastdiv((uint32_t)s.W);
     t.geo = make_geo(s.H, s.W);
     t.allow_fast = (s.W > 1 && s.H > 1 && s.W <= 32768 && s.H <= 32768);
+    t.ds = pose ? pose->downscale[l] : 1.0f;
     t.inv_n = 1.0f / (float)((double)d->B * d->C * s.H * s.W);
     t.depth = s.depth;
     t.tgt = static_cast<const float*>(s.tgt);
@@ -138,7 +157,7 @@ DVF_EXPORT int dvf_photo_loss_fused(const dvf_loss_desc* d, const dvf_level* lev
       if (v < d->V && !s.src[v]) return DVF_EINVAL_NULL;
       if (t.gsrc[v]) need_grad = true;
     }
-    if (s.gdepth || s.gexpl || s.gtgt || s.gP) need_grad = true;
+    if (s.gdepth || s.gexpl || s.gtgt || s.gP || (pose && pose->gvec)) need_grad = true;
     if (s.gexpl && !s.expl) return DVF_EINVAL_NULL;
     t.block_begin = pl.block_begin[l];
     t.blocks_per_image = pl.blocks_per_image[l];
@@ -149,6 +168,8 @@ DVF_EXPORT int dvf_photo_loss_fused(const dvf_loss_desc* d, const dvf_level* lev
     t.lvl_counter = reinterpret_cast<unsigned*>(ws + pl.off_lcnt[l]);
   }
   prm.need_grad = need_grad;
+  prm.gM_ws = reinterpret_cast<double*>(ws + pl.off_gM);
+  prm.pose_counter = reinterpret_cast<unsigned*>(ws + pl.off_pcnt);
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   const int nb = pl.total_blocks;
 #define DVF_DISPATCH_V(FN, Z)                                  \
@@ -185,4 +206,15 @@ DVF_EXPORT int dvf_photo_loss_fused(const dvf_loss_desc* d, const dvf_level* lev
   }
 #undef DVF_DISPATCH_V
   return launch_status();
+}
+
+DVF_EXPORT int dvf_photo_loss_fused(const dvf_loss_desc* d, const dvf_level* levels, float* terms, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  return run_loss(d, levels, nullptr, terms, workspace, workspace_bytes, stream);
+}
+
+DVF_EXPORT int dvf_photo_loss_fused_pose(const dvf_loss_desc* d, const dvf_level* levels, const dvf_pose_args* pose,
+                                         float* terms, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!pose) return DVF_EINVAL_NULL;
+  return run_loss(d, levels, pose, terms, workspace, workspace_bytes, stream);
 }

@@ -23,6 +23,7 @@
 #include "dvf_internal.h"
 #include "dvf_math.cuh"
 #include "dvf_math2.cuh"
+#include "dvf_pose.cuh"
 #include "dvf_reduce.cuh"
 #include "dvf_tma.cuh"
 
@@ -36,6 +37,7 @@ struct LevelDev {
   FastDiv divW;
   Geo geo;
   float inv_n;
+  float ds;           // downscale of this level (pose mode)
   int allow_fast;
   const float* depth;
   const float* tgt;
@@ -58,8 +60,15 @@ struct LevelDev {
 
 struct LossParams {
   int n_levels, B, C, V;
-  int need_grad, reserved;
+  int need_grad, rotation;
   float* terms;  // [n_levels*V]
+  // pose mode (dvf_photo_loss_fused_pose): P / K^-1_s are derived in the CTA prologue, d pose in the epilogue
+  const float* pose_vec;   // [B,V,6] or nullptr
+  const float* K;          // [B,3,3]
+  const float* Kinv;       // [B,3,3]
+  float* gvec;             // [B,V,6] or nullptr
+  double* gM_ws;           // [n_levels][B*V][12]  dL/d pose_mat per level
+  unsigned* pose_counter;  // [B] zero between launches
   LevelDev lv[DVF_MAX_LEVELS];
 };
 
@@ -77,6 +86,81 @@ static __device__ __noinline__ ChainGrad chain_backward_exact(const float* P /*s
   return o;
 }
 
+// out-of-line so that their register / stack needs (sinf/cosf slow paths, fp64) stay out of the pixel loop
+static __device__ __noinline__ float trig_of(float a, int want_sin) { return want_sin ? sinf(a) : cosf(a); }
+static __device__ __noinline__ void level_gM(const float* K, float ds, const float* gP /*12, smem*/, double* dst) {
+  float Ks[9];
+  scaled_K(K, ds, Ks);
+  double gM[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) gM[q] = 0.0;
+  accumulate_gM(Ks, gP, gM);
+#pragma unroll
+  for (int q = 0; q < 12; ++q) __stcg(dst + q, gM[q]);
+}
+static __device__ __noinline__ double dtrig_of(double a, int want_cos) { return want_cos ? cos(a) : sin(a); }
+// d(sum gR * Rx Ry Rz)/d angle `which` (0 = x, 1 = y, 2 = z), fp64; tr = (sx, cx, sy, cy, sz, cz)
+static __device__ __noinline__ float euler_angle_grad(const double* gM /*3x4*/, const double* tr, int which) {
+  const double sx = tr[0], cx = tr[1], sy = tr[2], cy = tr[3], sz = tr[4], cz = tr[5];
+  double Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx}, Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy}, Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
+  if (which == 0) { const double d[9] = {0, 0, 0, 0, -sx, -cx, 0, cx, -sx}; for (int q = 0; q < 9; ++q) Rx[q] = d[q]; }
+  if (which == 1) { const double d[9] = {-sy, 0, cy, 0, 0, 0, -cy, 0, -sy}; for (int q = 0; q < 9; ++q) Ry[q] = d[q]; }
+  if (which == 2) { const double d[9] = {-sz, -cz, 0, cz, -sz, 0, 0, 0, 0}; for (int q = 0; q < 9; ++q) Rz[q] = d[q]; }
+  double t1[9], t2[9], gR[9];
+  dmm3(Rx, Ry, t1);
+  dmm3(t1, Rz, t2);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) gR[r * 3 + c] = gM[r * 4 + c];
+  return (float)ddot9(gR, t2);
+}
+
+// CTA prologue: projection matrices of image b at this level into shared memory -- either read from the
+// arrays the caller computed (dvf_pose_proj_fwd) or derived here from the 6-DoF vectors (same routines).
+template <int kV>
+__device__ __forceinline__ void load_matrices(const LossParams& prm, const LevelDev& lv, int b, float (*s_P)[12], float* s_M) {
+  const int tid = threadIdx.x;
+  if (prm.pose_vec) {
+    // Three short stages, each spread over threads so that the prologue costs one global-load latency plus a
+    // few hundred cycles: (1) fetch vec / K / K^-1, (2) sinf/cosf and the level's scaled intrinsics,
+    // (3) every thread of the first kV*12 composes R and takes one entry of P = K_s @ [R|t].
+    // Operation order per entry is identical to dvf_pose_proj_fwd.
+    __shared__ float s_vec[kV][6];
+    __shared__ float s_trig[kV][6];
+    __shared__ float s_Ks[9];
+    const bool euler = prm.rotation == DVF_ROT_EULER;
+    if (tid < kV * 6) s_vec[tid / 6][tid % 6] = prm.pose_vec[((size_t)b * kV + tid / 6) * 6 + tid % 6];
+    else if (tid >= 32 && tid < 41) s_Ks[tid - 32] = prm.K[b * 9 + (tid - 32)];
+    else if (tid >= 64 && tid < 73) s_M[tid - 64] = prm.Kinv[b * 9 + (tid - 64)];
+    __syncthreads();
+    if (tid < kV * 6) {
+      if (euler) {
+        const int v = tid / 6, q = tid % 6;           // q: 0 cz, 1 sz, 2 cy, 3 sy, 4 cx, 5 sx
+        s_trig[v][q] = trig_of(s_vec[v][3 + (2 - q / 2)], q & 1);
+      }
+    } else if (tid >= 32 && tid < 41) {
+      const int q = tid - 32;
+      if (q < 6 && lv.ds != 1.0f) s_Ks[q] = div(s_Ks[q], lv.ds);               // rows 0-1 / downscale
+    } else if (tid >= 64 && tid < 73) {
+      const int q = tid - 64;
+      if ((q % 3) < 2 && lv.ds != 1.0f) s_M[q] = mul(s_M[q], lv.ds);          // columns 0-1 * downscale
+    }
+    __syncthreads();
+    if (tid < kV * 12) {
+      const int v = tid / 12, r = (tid % 12) / 4, c = tid % 4;
+      float R[9];
+      if (euler) euler_compose(s_vec[v][5], s_trig[v][0], s_trig[v][1], s_trig[v][2], s_trig[v][3], s_trig[v][4], s_trig[v][5], R);
+      else rotation_fwd(&s_vec[v][3], prm.rotation, R);
+      const float p0 = c < 3 ? R[0 * 3 + (c < 3 ? c : 0)] : s_vec[v][0];
+      const float p1 = c < 3 ? R[1 * 3 + (c < 3 ? c : 0)] : s_vec[v][1];
+      const float p2 = c < 3 ? R[2 * 3 + (c < 3 ? c : 0)] : s_vec[v][2];
+      s_P[v][r * 4 + c] = add(add(mul(s_Ks[r * 3 + 0], p0), mul(s_Ks[r * 3 + 1], p1)), mul(s_Ks[r * 3 + 2], p2));
+    }
+  } else {
+    if (tid < kV * 12) s_P[tid / 12][tid % 12] = lv.P[((size_t)b * kV + tid / 12) * 12 + tid % 12];
+    if (tid >= 64 && tid < 73) s_M[tid - 64] = lv.Kinv[b * 9 + (tid - 64)];
+  }
+}
+
 // sign(d)/N with sign(0) = sign(NaN) = 0, gated by `gate`
 __device__ __forceinline__ float signed_unit(float d, float inv_n, bool gate) {
   const bool nz = (d < 0.0f || d > 0.0f) && gate;
@@ -90,6 +174,7 @@ __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], c
   __shared__ float s_red[kThreadsT / 32][kV][kRedSlots];
   __shared__ int s_flag;
   __shared__ double s_term[kThreadsT / 32];
+  __shared__ float s_gp[kV][12];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int v = 0; v < kV; ++v) {
@@ -120,6 +205,7 @@ __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], c
     if ((tid & 7) == 0) {
       if (s < 12) {
         if (lv.gP) lv.gP[((size_t)b * kV + v) * 12 + s] = (float)sum;
+        s_gp[v][s] = (float)sum;
       } else if (s == 12) {
         lv.img_terms[(size_t)b * kV + v] = sum;
       }
@@ -127,6 +213,52 @@ __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], c
   }
   __threadfence();
   __syncthreads();
+  if (prm.gvec) {
+    // pose mode: dL/d pose_mat of this level = K_s^T @ dL/dP (fp64); the level that finishes LAST for image b
+    // adds the levels in fixed order and runs the analytic backward of pose_vec2mat
+    if (tid < kV) {
+      level_gM(prm.K + b * 9, lv.ds, &s_gp[tid][0], prm.gM_ws + (((size_t)l * prm.B + b) * kV + tid) * 12);
+      __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const bool last_level = atomicAdd(prm.pose_counter + b, 1u) == (unsigned)(prm.n_levels - 1);
+      if (last_level) prm.pose_counter[b] = 0u;
+      s_flag = last_level;
+    }
+    __syncthreads();
+    if (s_flag) {
+      // this sits at the tail of the kernel: spread it over threads instead of one long fp64 chain per view
+      __threadfence();
+      __shared__ double s_gM[kV][12];
+      __shared__ double s_dtrig[kV][6];
+      const bool euler = prm.rotation == DVF_ROT_EULER;
+      if (tid < kV * 12) {
+        const int v = tid / 12, q = tid % 12;
+        double s = 0.0;
+        for (int ll = 0; ll < prm.n_levels; ++ll) s += __ldcg(prm.gM_ws + (((size_t)ll * prm.B + b) * kV + v) * 12 + q);
+        s_gM[v][q] = s;
+      } else if (euler && tid >= 64 && tid < 64 + kV * 6) {
+        const int v = (tid - 64) / 6, q = (tid - 64) % 6;        // q: 0 sx, 1 cx, 2 sy, 3 cy, 4 sz, 5 cz
+        s_dtrig[v][q] = dtrig_of((double)prm.pose_vec[((size_t)b * kV + v) * 6 + 3 + q / 2], q & 1);
+      }
+      __syncthreads();
+      if (tid < kV * 6) {
+        const int v = tid / 6, q = tid % 6;
+        float* gv = prm.gvec + ((size_t)b * kV + v) * 6;
+        if (q < 3) {
+          gv[q] = (float)s_gM[v][q * 4 + 3];                      // translation: last column of dL/d pose_mat
+        } else if (euler) {
+          gv[q] = euler_angle_grad(&s_gM[v][0], &s_dtrig[v][0], q - 3);
+        } else if (q == 3) {
+          float g6[6];
+          posemat_bwd(&s_gM[v][0], prm.pose_vec + ((size_t)b * kV + v) * 6, prm.rotation, g6);
+          gv[3] = g6[3]; gv[4] = g6[4]; gv[5] = g6[5];
+        }
+      }
+    }
+    __syncthreads();
+  }
   if (tid == 0) {
     lv.img_counter[b] = 0u;
     s_flag = (atomicAdd(lv.lvl_counter, 1u) == (unsigned)(prm.B - 1));
@@ -178,8 +310,7 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3_kernel
   const FastDiv divW = lv.divW;
   const float inv_n = lv.inv_n;
 
-  if (tid < kV * 12) s_P[tid / 12][tid % 12] = lv.P[((size_t)b * kV + tid / 12) * 12 + tid % 12];
-  if (tid >= 64 && tid < 73) s_M[tid - 64] = lv.Kinv[b * 9 + (tid - 64)];
+  load_matrices<kV>(prm, lv, b, s_P, s_M);
   __syncthreads();
 
   float acc[kV][kRedSlots];
@@ -323,14 +454,11 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   const FastDiv divW = lv.divW;
   const float inv_n = lv.inv_n;
 
-  if (tid < kV * 12) s_P[tid / 12][tid % 12] = lv.P[((size_t)b * kV + tid / 12) * 12 + tid % 12];
-  if (tid >= 64 && tid < 73) s_M[tid - 64] = lv.Kinv[b * 9 + (tid - 64)];
   if (kTma && tid == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
     mbar_fence_init();
   }
-  __syncthreads();
 
   f2 acc2[kV][12];     // dL/dP partial sums, (A,B) lanes folded at the end
   float accl[kV];      // loss partial sums
@@ -347,19 +475,6 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   const bool want_gdepth = lv.gdepth != nullptr;
   const float* const expl_b = kExpl ? lv.expl + (size_t)b * lv.expl_bstride : nullptr;
   float* const gexpl_b = (kExpl && lv.gexpl) ? lv.gexpl + (size_t)b * kV * HW : nullptr;
-  bool mats_ok = lv.allow_fast != 0;
-  float M[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    M[k] = s_M[k];
-    mats_ok = mats_ok && (fabsf(M[k]) <= 1048576.0f);
-  }
-#pragma unroll
-  for (int v = 0; v < kV; ++v)
-#pragma unroll
-    for (int k = 0; k < 12; ++k) mats_ok = mats_ok && (fabsf(s_P[v][k]) <= 1073741824.0f);
-  const float depth_max = mats_ok ? 1073741824.0f : -1.0f;   // see photo_loss_c3_kernel
-
   const float* src_b[kV];
 #pragma unroll
   for (int v = 0; v < kV; ++v) src_b[v] = lv.src[v] + (size_t)b * kC * HW;
@@ -399,6 +514,23 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   if (kTma && tid == 0) {
     for (int k = 0; k < min(kStages, n_chunks); ++k) issue(k);
   }
+
+  // projection matrices of this image (overlaps with the bulk copies just issued)
+  load_matrices<kV>(prm, lv, b, s_P, s_M);
+  __syncthreads();
+  bool mats_ok = lv.allow_fast != 0;
+  float M[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    M[k] = s_M[k];
+    mats_ok = mats_ok && (fabsf(M[k]) <= 1048576.0f);
+  }
+#pragma unroll
+  for (int v = 0; v < kV; ++v)
+#pragma unroll
+    for (int k = 0; k < 12; ++k) mats_ok = mats_ok && (fabsf(s_P[v][k]) <= 1073741824.0f);
+  const float depth_max = mats_ok ? 1073741824.0f : -1.0f;   // see photo_loss_c3_kernel
+
 
   // one chunk; kTail = the chunk may contain lanes past the end of the run (only the last chunk can)
   auto do_chunk = [&](int k, auto tail_tag) {
@@ -625,8 +757,7 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_cn_kernel(const __
   const bool has_expl = lv.expl != nullptr;
   const float inv_n = lv.inv_n;
 
-  if (tid < kV * 12) s_P[tid / 12][tid % 12] = lv.P[((size_t)b * kV + tid / 12) * 12 + tid % 12];
-  if (tid >= 64 && tid < 73) s_M[tid - 64] = lv.Kinv[b * 9 + (tid - 64)];
+  load_matrices<kV>(prm, lv, b, s_P, s_M);
   __syncthreads();
 
   float acc[kV][kRedSlots];

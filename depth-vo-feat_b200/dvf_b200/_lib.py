@@ -37,6 +37,11 @@ class dvf_level(C.Structure):
                 ("gtgt", C.c_void_p), ("gP", C.c_void_p)]
 
 
+class dvf_pose_args(C.Structure):
+    _fields_ = [("vec", C.c_void_p), ("K", C.c_void_p), ("Kinv", C.c_void_p), ("downscale", C.POINTER(C.c_float)),
+                ("rotation", C.c_int32), ("reserved", C.c_int32), ("gvec", C.c_void_p)]
+
+
 class dvf_loss_desc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("V", C.c_int32), ("n_levels", C.c_int32),
                 ("dtype", C.c_int32), ("layout", C.c_int32), ("padding", C.c_int32), ("reserved", C.c_int32)]
@@ -57,6 +62,8 @@ SIGNATURES = {
     "dvf_inverse_warp_bwd": (C.c_int, [C.POINTER(dvf_desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dvf_photo_loss_workspace_bytes": (_sz, [C.POINTER(dvf_loss_desc), C.POINTER(dvf_level)]),
     "dvf_photo_loss_fused": (C.c_int, [C.POINTER(dvf_loss_desc), C.POINTER(dvf_level), _vp, _vp, _sz, _vp]),
+    "dvf_photo_loss_fused_pose": (C.c_int, [C.POINTER(dvf_loss_desc), C.POINTER(dvf_level), C.POINTER(dvf_pose_args), _vp, _vp,
+                                            _sz, _vp]),
     "dvf_area_pyramid": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "dvf_area_downsample": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "dvf_selftest_fast_div": (C.c_int, [C.c_uint64, C.c_uint64, _i32, _vp, _vp]),

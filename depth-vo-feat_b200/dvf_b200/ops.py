@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import DvfError, PADDING, ROTATION, dvf_desc, dvf_level, dvf_loss_desc
+from ._lib import DvfError, PADDING, ROTATION, dvf_desc, dvf_level, dvf_loss_desc, dvf_pose_args
 
 _WS = {}
 
@@ -283,8 +283,12 @@ class FusedPhotoLoss(torch.autograd.Function):
         B, Cc = tgts[0].shape[0], tgts[0].shape[1]
         dev = pose.device
         vec = pose.reshape(B * V, 6)
-        _, P, Kinv_s = pose_proj_fwd(vec, K, Kinv, V, cfg.rotation_mode, cfg.downscales)
-        gP = torch.empty(L, B * V, 3, 4, device=dev, dtype=torch.float32) if need_pose else None
+        # the kernel derives P and K^-1_s from the pose itself and finishes with the pose backward (one launch);
+        # dP is only materialised for the pose gradient, inside the kernel's workspace
+        g_pose = torch.empty(B, V, 6, device=dev, dtype=torch.float32) if need_pose else None
+        ds_arr = (C.c_float * L)(*[float(x) for x in cfg.downscales])
+        pargs = dvf_pose_args(vec.data_ptr(), K.data_ptr(), Kinv.data_ptr(), ds_arr, ROTATION[cfg.rotation_mode], 0,
+                              _ptr(g_pose))
         terms = torch.empty(L * V, device=dev, dtype=torch.float32)
 
         levels = (dvf_level * L)()
@@ -297,7 +301,6 @@ class FusedPhotoLoss(torch.autograd.Function):
                 raise AssertionError(f"level {l}: target {list(tgts[l].shape)} does not match depth {list(depths[l].shape)}")
             lv.H, lv.W = h, w
             lv.depth, lv.tgt = depths[l].data_ptr(), tgts[l].data_ptr()
-            lv.P, lv.Kinv = P[l].data_ptr(), Kinv_s[l].data_ptr()
             for v in range(V):
                 s = srcs[l * V + v]
                 if s.shape != tgts[l].shape:
@@ -321,18 +324,13 @@ class FusedPhotoLoss(torch.autograd.Function):
             if need_tgt[l]:
                 g_tgt[l] = torch.empty_like(tgts[l])
                 lv.gtgt = g_tgt[l].data_ptr()
-            if need_pose:
-                lv.gP = gP[l].data_ptr()
         d = dvf_loss_desc(B, Cc, V, L, _lib.F32, _lib.NCHW, PADDING[cfg.padding_mode], 0)
         nbytes = lib.dvf_photo_loss_workspace_bytes(C.byref(d), levels)
         if nbytes == 0:
             raise DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")
         ws = workspace(nbytes, dev, ('loss', B, Cc, V, cfg.has_expl) + tuple(tuple(x.shape[1:]) for x in depths))
-        _lib.check(lib.dvf_photo_loss_fused(C.byref(d), levels, _ptr(terms), _ptr(ws), ws.numel(), _stream()),
-                   "dvf_photo_loss_fused")
-        g_pose = None
-        if need_pose:
-            g_pose = pose_proj_bwd(gP, None, vec, K, V, cfg.rotation_mode, cfg.downscales).reshape(B, V, 6)
+        _lib.check(lib.dvf_photo_loss_fused_pose(C.byref(d), levels, C.byref(pargs), _ptr(terms), _ptr(ws), ws.numel(),
+                                                 _stream()), "dvf_photo_loss_fused_pose")
         for l in range(L):
             if cfg.has_expl and need_expl[l] and expls[l].shape[1] > V:
                 full = torch.zeros_like(expls[l])

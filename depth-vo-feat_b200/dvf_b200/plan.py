@@ -1,10 +1,11 @@
 """Static-shape execution plan for the fused reconstruction loss: allocate once, launch many times.
 
-A training loop with fixed shapes binds its tensors once and then issues exactly three launches per
-step through the C ABI -- dvf_pose_proj_fwd, dvf_photo_loss_fused (all levels and views, forward +
-backward), dvf_pose_proj_bwd -- optionally captured into a CUDA graph so a step costs one graph
-launch.  No autograd bookkeeping, no allocation, no host synchronisation.  Gradients are those of
-`sum of loss terms` (upstream gradient 1), exactly what loss.backward() yields for the reference's
+A training loop with fixed shapes binds its tensors once and then issues ONE launch per step through the
+C ABI -- dvf_photo_loss_fused_pose: pose_vec2mat and projection in the kernel prologue, warp + loss + all
+gradients for every level and view, pose backward in the epilogue -- optionally replayed from a CUDA graph.
+(The three-launch form dvf_pose_proj_fwd / dvf_photo_loss_fused / dvf_pose_proj_bwd is kept for callers
+that supply their own projection matrices.)  No autograd bookkeeping, no allocation, no host
+synchronisation.  Gradients are those of `sum of loss terms` (upstream gradient 1), exactly what loss.backward() yields for the reference's
 photometric_reconstruction_loss (loss_functions_sfm.py:9-46 / loss_functions.py:7-20).
 """
 from __future__ import annotations
@@ -15,7 +16,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import PADDING, ROTATION, dvf_level, dvf_loss_desc
+from ._lib import PADDING, ROTATION, dvf_level, dvf_loss_desc, dvf_pose_args
 
 
 class FusedLossPlan:
@@ -64,8 +65,13 @@ class FusedLossPlan:
             raise _lib.DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")
         self.ws = torch.zeros(n, dtype=torch.uint8, device=dev)   # private workspace: plans may be in flight together
         self.warped_px = sum(B * V * d.shape[1] * d.shape[2] for d in depth_levels)
-        self.n_launches = 3 if need_grad else 2
         self.need_grad = need_grad
+        # single-launch form: pose -> P in the kernel prologue, d pose in its epilogue
+        self.pose_args = dvf_pose_args(pose.data_ptr(), K.data_ptr(), Kinv.data_ptr(), self.ds, self.rotation, 0,
+                                       self.gpose.data_ptr() if need_grad else None)
+        import os
+        self.fused_pose = os.environ.get("DVF_PLAN_FUSED_POSE", "1") != "0"   # 0: three-launch form (debug / A-B timing)
+        self.n_launches = 1 if self.fused_pose else (3 if need_grad else 2)
 
     # -- the three launches ---------------------------------------------------------------------
     def launch_pose_fwd(self, stream: int):
@@ -84,8 +90,17 @@ class FusedLossPlan:
                                               self.rotation, self.ds, self.L, self.gpose.data_ptr(), stream),
                    "dvf_pose_proj_bwd")
 
-    def launch(self, stream: Optional[int] = None):
+    def launch_fused(self, stream: int):
+        """ONE launch: pose_vec2mat + projection, warp + loss + all gradients, pose backward."""
+        _lib.check(self.lib.dvf_photo_loss_fused_pose(C.byref(self.desc), self.levels, C.byref(self.pose_args),
+                                                      self.terms.data_ptr(), self.ws.data_ptr(), self.ws.numel(), stream),
+                   "dvf_photo_loss_fused_pose")
+
+    def launch(self, stream: Optional[int] = None, fused_pose: Optional[bool] = None):
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        if self.fused_pose if fused_pose is None else fused_pose:
+            self.launch_fused(st)
+            return
         self.launch_pose_fwd(st)
         self.launch_loss(st)
         if self.need_grad:
@@ -97,10 +112,10 @@ class FusedLossPlan:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            if loss_only:
+            if loss_only and not self.fused_pose:
                 self.launch_loss(torch.cuda.current_stream().cuda_stream)
             else:
-                self.launch()
+                self.launch()   # fused-pose form: the step IS the one loss kernel
         return g
 
     def loss(self) -> torch.Tensor:

@@ -155,6 +155,22 @@ int dvf_photo_loss_fused(const dvf_loss_desc* d, const dvf_level* levels,
                          float* terms, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* Same launch with the pose chain folded in: the kernel derives P = (K rows 0-1 / downscale) @ pose_vec2mat(vec)
+ * and K^-1_s itself (levels[l].P / .Kinv are ignored, may be NULL) and, when gvec is given, finishes with the
+ * backward of pose_vec2mat -> d(sum of terms)/d vec, summed over levels.  One launch per training step.      */
+typedef struct dvf_pose_args {
+  const float* vec;        /* [B,V,6] (tx,ty,tz,rx,ry,rz)                                     */
+  const float* K;          /* [B,3,3]                                                         */
+  const float* Kinv;       /* [B,3,3]                                                         */
+  const float* downscale;  /* HOST array [n_levels]: image H / level h (loss_functions_sfm.py:16) */
+  int32_t rotation;        /* dvf_rotation                                                    */
+  int32_t reserved;
+  float* gvec;             /* [B,V,6] written, or NULL                                        */
+} dvf_pose_args;
+
+int dvf_photo_loss_fused_pose(const dvf_loss_desc* d, const dvf_level* levels, const dvf_pose_args* pose,
+                              float* terms, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- neighbours of the path ----------------------------
  * F.interpolate(img,(h,w),mode='area') for the integer factors 2,4,8
  * (loss_functions_sfm.py:18-19): one pass over img writes all levels.        */

@@ -375,3 +375,34 @@ def test_errors_are_loud(ops, syn):
     with pytest.raises(AssertionError):   # reference's size check (inverse_warp.py:173)
         iw.inverse_warp(d["img_R1"].cuda()[:, :2], d["depth"].cuda(), d["T_2to1"].cuda(), d["intrinsics"].cuda(),
                         d["intrinsics_inv"].cuda())
+
+
+def test_fused_pose_entry_matches_three_launch_form(ops, syn):
+    """dvf_photo_loss_fused_pose (pose chain inside the kernel) == pose_proj_fwd + photo_loss_fused + pose_proj_bwd,
+    bit for bit, multi-level, V=2, with masks."""
+    from dvf_b200.plan import FusedLossPlan
+    B, H, W, V, L = 3, 64, 208, 2, 3
+    d = syn.stereo_temporal_batch(B, H, W, seed=91)
+    sizes = [(H >> s, W >> s) for s in range(L)]
+    tg = ops.area_pyramid(d["img_R2"].cuda(), sizes)
+    r1 = ops.area_pyramid(d["img_R1"].cuda(), sizes)
+    l2 = ops.area_pyramid(d["img_L2"].cuda(), sizes)
+    depths = [syn.depth(B, h, w, 100 + i).cuda() for i, (h, w) in enumerate(sizes)]
+    expl = [syn.explainability(B, V, h, w, 110 + i).cuda() for i, (h, w) in enumerate(sizes)]
+    pose = torch.stack([d["T_2to1"], d["T_R2L"]], 1).cuda().contiguous()
+    for rot in ("euler", "quat"):
+        plan = FusedLossPlan(tg, [[r1[s], l2[s]] for s in range(L)], depths, pose, d["intrinsics"].cuda(),
+                             d["intrinsics_inv"].cuda(), expl_levels=expl, downscales=[float(1 << s) for s in range(L)],
+                             rotation_mode=rot)
+        outs = []
+        for fused in (False, True, True):
+            plan.terms.fill_(-1); plan.gpose.fill_(-1)
+            for g in plan.gdepth + plan.gexpl:
+                g.fill_(-1)
+            plan.launch(fused_pose=fused)
+            torch.cuda.synchronize()
+            outs.append([plan.terms.clone(), plan.gpose.clone()] + [g.clone() for g in plan.gdepth + plan.gexpl])
+        for other in outs[1:]:
+            for a, b in zip(outs[0], other):
+                assert torch.equal(a, b)
+        assert float(outs[0][0].min()) > 0
