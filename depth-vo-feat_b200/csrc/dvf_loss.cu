@@ -49,9 +49,9 @@ static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) 
     if ((long long)levels[l].H * levels[l].W >= (1ll << 30)) return DVF_EINVAL_SHAPE;
     total_px += (long long)levels[l].H * levels[l].W * d->B;
   }
-  // aim for >= ~16 CTAs per SM over the whole launch; 1..16 chunks of kLossThreads*kPPT px per CTA
+  // aim for ~6 CTAs per SM over the whole launch (4 resident): fixed per-CTA cost vs tail balance
   const long long chunk = (long long)kLossThreads * plan_ppt(d, levels);
-  const long long want_blocks = 16ll * num_sms();
+  const long long want_blocks = 6ll * num_sms();   // measured flat between 4 and 16 CTAs per SM (profiles/r1_summary.md)
   int iters = (int)(total_px / (chunk * want_blocks));
   if (iters < 1) iters = 1;
   if (iters > 64) iters = 64;

@@ -606,7 +606,11 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
       }
       locate2<kZeros>(pr.xn, pr.yn, H, W, geo, geo2, L);
 
+#if defined(DVF_EXP_NOGATHER)
+      const int oA = min(idxA, HW - W - 2), oB = min(idxB, HW - W - 2);   // experiment: coalesced instead of gathered taps
+#else
       const int oA = L.y0A * W + L.x0A, oB = L.y0B * W + L.x0B;
+#endif
       const bool nwA = L.nwA && liveA, neA = L.neA && liveA, swA = L.swA && liveA, seA = L.seA && liveA;
       const bool nwB = L.nwB && liveB, neB = L.neB && liveB, swB = L.swB && liveB, seB = L.seB && liveB;
       f2 t00[kC], t01[kC], t10[kC], t11[kC];

@@ -14,7 +14,7 @@ import sys
 PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # depth-vo-feat_b200/
 CSRC = os.path.join(PKG_ROOT, "csrc")
 LIB_DIR = os.path.join(PKG_ROOT, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libdvf_b200.so")
+LIB_PATH = os.path.join(LIB_DIR, os.environ.get("DVF_LIB_NAME", "libdvf_b200.so"))   # DVF_LIB_NAME: experiment builds
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -45,7 +45,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libdvf_b200.so cannot be built (there is no non-CUDA fallback)")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    extra = os.environ.get("DVF_EXTRA_NVCC_FLAGS", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(res.stderr)
