@@ -8,7 +8,7 @@
 // (4 + 4C + 4)/V + 4C bytes per warped pixel for fp32 NCHW (32 B at C=3, V=1).
 #include <stdlib.h>
 
-#include "dvf_loss_kernel.cuh"
+#include "dvf_loss_nhwc.cuh"
 
 namespace dvf {
 
@@ -27,7 +27,7 @@ struct Plan {
 
 // pixels per thread per iteration of the kernel that will run (must match dvf_loss_inst_*.cu)
 static bool uses_c3_kernel(const dvf_loss_desc* d, const dvf_level* levels) {
-  if (d->C != 3) return false;
+  if (d->C != 3 || d->layout != DVF_NCHW || d->dtype != DVF_F32) return false;
   for (int l = 0; l < d->n_levels; ++l) {   // the register-resident image kernel has no scatter / d-target outputs
     if (levels[l].gtgt) return false;
     for (int v = 0; v < d->V && v < DVF_MAX_VIEWS; ++v)
@@ -100,7 +100,16 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
   int st = make_plan(d, levels, pl);
   if (st != DVF_OK) return st;
   if (!terms) return DVF_EINVAL_NULL;
-  if (d->dtype != DVF_F32 || d->layout != DVF_NCHW) return DVF_EUNSUPPORTED;
+  if (d->dtype != DVF_F32 && d->dtype != DVF_BF16) return DVF_EINVAL_DTYPE;
+  if (d->layout != DVF_NCHW && d->layout != DVF_NHWC) return DVF_EINVAL_DTYPE;
+  const bool nhwc = d->layout == DVF_NHWC;
+  const bool bf16 = d->dtype == DVF_BF16;
+  if (bf16 && !nhwc) return DVF_EUNSUPPORTED;                 // bf16 maps are channels-last only
+  if (nhwc) {
+    const int vec = bf16 ? 8 : 4;
+    const int lpp = d->C / vec;
+    if (d->C % vec != 0 || lpp < 1 || lpp > 32 || (lpp & (lpp - 1)) != 0) return DVF_EUNSUPPORTED;   // C = vec * 2^k
+  }
   if (d->padding != DVF_PAD_ZEROS && d->padding != DVF_PAD_BORDER) return DVF_EINVAL_DTYPE;
   if (!workspace || workspace_bytes < pl.bytes) return DVF_EWORKSPACE;
   if (!aligned(workspace, 256)) return DVF_EINVAL_ALIGN;
@@ -133,6 +142,7 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     if (!s.depth || !s.tgt) return DVF_EINVAL_NULL;
     if (!pose && (!s.P || !s.Kinv)) return DVF_EINVAL_NULL;
     if (!aligned(s.depth, 4) || !aligned(s.tgt, 4) || !aligned(s.P, 4) || !aligned(s.Kinv, 4)) return DVF_EINVAL_ALIGN;
+    if (nhwc && (!aligned(s.tgt, 16) || !aligned(s.gtgt, 16))) return DVF_EINVAL_ALIGN;
     t.H = s.H;
     t.W = s.W;
     t.HW = s.H * s.W;
@@ -155,6 +165,7 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
       t.src[v] = v < d->V ? static_cast<const float*>(s.src[v]) : nullptr;
       t.gsrc[v] = v < d->V ? static_cast<float*>(s.gsrc[v]) : nullptr;
       if (v < d->V && !s.src[v]) return DVF_EINVAL_NULL;
+      if (nhwc && v < d->V && (!aligned(s.src[v], 16) || !aligned(s.gsrc[v], 16))) return DVF_EINVAL_ALIGN;
       if (t.gsrc[v]) need_grad = true;
     }
     if (s.gdepth || s.gexpl || s.gtgt || s.gP || (pose && pose->gvec)) need_grad = true;
@@ -179,7 +190,17 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     case 3: FN<3, Z>(prm, nb, cs); break;                      \
     default: FN<4, Z>(prm, nb, cs); break;                     \
   }
-  if (uses_c3_kernel(d, levels)) {
+  if (nhwc) {
+#define DVF_DISPATCH_NHWC(Z)                                        \
+  switch (d->V) {                                                   \
+    case 1: launch_loss_nhwc<1, Z>(prm, nb, bf16, cs); break;       \
+    case 2: launch_loss_nhwc<2, Z>(prm, nb, bf16, cs); break;       \
+    case 3: launch_loss_nhwc<3, Z>(prm, nb, bf16, cs); break;       \
+    default: launch_loss_nhwc<4, Z>(prm, nb, bf16, cs); break;      \
+  }
+    if (zeros) { DVF_DISPATCH_NHWC(true) } else { DVF_DISPATCH_NHWC(false) }
+#undef DVF_DISPATCH_NHWC
+  } else if (uses_c3_kernel(d, levels)) {
     bool expl = false;
     for (int l = 0; l < d->n_levels; ++l) expl |= (levels[l].expl != nullptr);
     for (int l = 0; l < d->n_levels; ++l)

@@ -41,6 +41,39 @@ def _req(t, name, ndim=None):
     return t.contiguous()
 
 
+def _nhwc_ok(t: torch.Tensor) -> bool:
+    """True if `t` ([B,C,H,W] view) is physically channels-last and its channel count suits the NHWC kernel
+    (16 bytes of channels per lane, a power-of-two number of lanes <= 32 per pixel)."""
+    if t.dim() != 4 or t.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    if t.is_contiguous() or not t.is_contiguous(memory_format=torch.channels_last):
+        return False
+    vec = 8 if t.dtype == torch.bfloat16 else 4
+    C_ = t.shape[1]
+    lpp = C_ // vec
+    return C_ % vec == 0 and 1 <= lpp <= 32 and (lpp & (lpp - 1)) == 0 and t.data_ptr() % 16 == 0
+
+
+def _req_maps(maps, name):
+    """Image / feature tensors of one loss call -> (tensors, layout, dtype).  Channels-last fp32 / bf16 maps go to
+    the NHWC kernel as they are; anything else is brought to dense NCHW fp32 (the reference layout)."""
+    for t in maps:
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+        if not t.is_cuda:
+            raise DvfError(f"{name} is on {t.device}: dvf_b200 is CUDA-only (sm_100a); there is no CPU fallback")
+        if t.dim() != 4:
+            raise AssertionError(f"wrong size for {name}, expected 4 dims, got {list(t.size())}")
+    if all(_nhwc_ok(t) for t in maps) and len({t.dtype for t in maps}) == 1:
+        return list(maps), _lib.NHWC, (_lib.BF16 if maps[0].dtype == torch.bfloat16 else _lib.F32)
+    out = []
+    for t in maps:
+        if t.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            raise DvfError(f"{name}: dtype {t.dtype} not supported")
+        out.append(t.float().contiguous())
+    return out, _lib.NCHW, _lib.F32
+
+
 def workspace(nbytes: int, device: torch.device, signature) -> torch.Tensor:
     """Zero-initialised scratch, one per (device, stream, call signature).  The kernels restore the
     ticket counters they use, so a workspace is reusable by later calls WITH THE SAME SHAPES; a call
@@ -269,8 +302,9 @@ class FusedPhotoLoss(torch.autograd.Function):
         K, Kinv = _req(K, "intrinsics", 3), _req(Kinv, "intrinsics_inv", 3)
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             raise DvfError("gradients w.r.t. the camera intrinsics are not implemented (unused by the reference)")
-        tgts = [_req(t, "tgt", 4) for t in tensors[0:L]]
-        srcs = [_req(t, "src", 4) for t in tensors[L:L + L * V]]
+        maps, layout, dtype = _req_maps(list(tensors[0:L + L * V]), "tgt/src")
+        tgts, srcs = maps[0:L], maps[L:L + L * V]
+        in_dtypes = [t.dtype for t in tensors[0:L + L * V]]
         depths = [_req(t, "depth", 3) for t in tensors[L + L * V:2 * L + L * V]]
         expls = [_req(t, "explainability_mask", 4) for t in tensors[2 * L + L * V:]] if cfg.has_expl else []
         off = 4  # index of the first *tensors entry in needs_input_grad
@@ -307,7 +341,7 @@ class FusedPhotoLoss(torch.autograd.Function):
                     raise AssertionError(f"level {l} view {v}: source {list(s.shape)} != target {list(tgts[l].shape)}")
                 lv.src[v] = s.data_ptr()
                 if need_src[l * V + v]:
-                    g_src[l * V + v] = torch.zeros_like(s)
+                    g_src[l * V + v] = torch.zeros_like(s, dtype=torch.float32)   # fp32, same memory format
                     lv.gsrc[v] = g_src[l * V + v].data_ptr()
             if cfg.has_expl:
                 e = expls[l]
@@ -322,9 +356,9 @@ class FusedPhotoLoss(torch.autograd.Function):
                 g_depth[l] = torch.empty_like(depths[l])
                 lv.gdepth = g_depth[l].data_ptr()
             if need_tgt[l]:
-                g_tgt[l] = torch.empty_like(tgts[l])
+                g_tgt[l] = torch.empty_like(tgts[l], dtype=torch.float32)
                 lv.gtgt = g_tgt[l].data_ptr()
-        d = dvf_loss_desc(B, Cc, V, L, _lib.F32, _lib.NCHW, PADDING[cfg.padding_mode], 0)
+        d = dvf_loss_desc(B, Cc, V, L, dtype, layout, PADDING[cfg.padding_mode], 0)
         nbytes = lib.dvf_photo_loss_workspace_bytes(C.byref(d), levels)
         if nbytes == 0:
             raise DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")
@@ -336,6 +370,9 @@ class FusedPhotoLoss(torch.autograd.Function):
                 full = torch.zeros_like(expls[l])
                 full[:, :V] = g_expl[l]
                 g_expl[l] = full
+        # gradients of the maps go back in the dtype the caller handed in
+        g_tgt = [g if g is None or g.dtype == in_dtypes[i] else g.to(in_dtypes[i]) for i, g in enumerate(g_tgt)]
+        g_src = [g if g is None or g.dtype == in_dtypes[L + i] else g.to(in_dtypes[L + i]) for i, g in enumerate(g_src)]
         ctx.unit_grads = [g_pose] + g_tgt + g_src + g_depth + (g_expl if cfg.has_expl else [])
         loss = terms.sum()
         ctx.mark_non_differentiable(terms)

@@ -406,3 +406,46 @@ def test_fused_pose_entry_matches_three_launch_form(ops, syn):
             for a, b in zip(outs[0], other):
                 assert torch.equal(a, b)
         assert float(outs[0][0].min()) > 0
+
+
+@pytest.mark.parametrize("dtype,C,V,with_expl", [("f32", 64, 2, False), ("f32", 32, 1, True), ("f32", 8, 2, False),
+                                                 ("bf16", 64, 2, False), ("bf16", 32, 2, True), ("bf16", 16, 1, False)])
+def test_feature_loss_channels_last_vs_oracle(ops, oracle, syn, dtype, C, V, with_expl):
+    """channels-last (NHWC) feature maps, fp32 and bf16: the NHWC kernel against the oracle.  bf16: maps are stored
+    in bf16, arithmetic and geometry in fp32 -> compared with the oracle on the bf16-rounded maps at 1e-2
+    (BASELINE north_star tolerance for bf16); fp32: 1e-5."""
+    B, H, W = 2, 32, 104
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    maps = [m.to(tdt) for m in syn.features(B, C, H, W, 17, n=V + 1)]
+    ref_maps = [m.float().numpy() for m in maps]                 # what the kernel actually reads
+    depth = syn.depth(B, H, W, 18)
+    kinds = ["kitti", "stereo"]
+    pose = torch.stack([syn.pose(B, kinds[v], 19 + v) for v in range(V)], 1)
+    K, Kinv = syn.intrinsics(B, H, W)
+    expl = syn.explainability(B, V, H, W, 21) if with_expl else None
+
+    cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)   # noqa: E731
+    t_maps = [cl(m).requires_grad_(True) for m in maps]
+    assert ops._nhwc_ok(t_maps[0])
+    t_depth = depth.cuda().requires_grad_(True)
+    t_pose = pose.cuda().requires_grad_(True)
+    t_expl = None if expl is None else expl.cuda().requires_grad_(True)
+    loss, terms = ops.fused_photo_loss([t_maps[0]], [t_maps[1:]], [t_depth], t_pose, K.cuda(), Kinv.cuda(),
+                                       expl_levels=None if expl is None else [t_expl])
+    loss.backward()
+    _, P_gpu, _ = ops.pose_proj_fwd(t_pose.detach().reshape(B * V, 6), K.cuda(), None, V, "euler", [1.0])
+    Pn = npy(P_gpu[0]).reshape(B, V, 3, 4)
+    r = oracle.photo_loss_P(ref_maps[0], ref_maps[1:], depth.numpy(), Pn, Kinv.numpy(),
+                            expl=None if expl is None else expl.numpy(), need_gsrc=True, need_gtgt=True)
+    tol_geo = RTOL_F32 if dtype == "f32" else 1e-4    # fp32 outputs; bf16 only changes what is read
+    tol_map = RTOL_F32 if dtype == "f32" else 1e-2    # map gradients come back in the map dtype
+    assert_close(npy(terms), r["terms"], tol=tol_geo, what="terms")
+    assert_close(npy(t_depth.grad), r["gdepth"], tol=tol_geo, what="gdepth")
+    assert t_maps[0].grad.dtype == tdt and t_maps[0].grad.is_contiguous(memory_format=torch.channels_last)
+    assert_close(npy(t_maps[0].grad.float()), r["gtgt"], tol=tol_map, what="gtgt")
+    for v in range(V):
+        assert_close(npy(t_maps[1 + v].grad.float()), r["gsrc"][v], tol=tol_map, what=f"gsrc{v}")
+        assert_close(npy(t_pose.grad[:, v]), oracle.pose_bwd(r["gP"][:, v], K.numpy(), pose[:, v].numpy()), tol=tol_geo,
+                     what=f"gpose{v}")
+    if with_expl:
+        assert_close(npy(t_expl.grad), r["gexpl"], tol=tol_geo, what="gexpl")
