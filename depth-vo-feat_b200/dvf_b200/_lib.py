@@ -42,6 +42,11 @@ class dvf_pose_args(C.Structure):
                 ("rotation", C.c_int32), ("reserved", C.c_int32), ("gvec", C.c_void_p)]
 
 
+class dvf_reg_level(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("g", C.c_void_p), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("weight", C.c_float)]
+
+
 class dvf_loss_desc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("V", C.c_int32), ("n_levels", C.c_int32),
                 ("dtype", C.c_int32), ("layout", C.c_int32), ("padding", C.c_int32), ("reserved", C.c_int32)]
@@ -66,6 +71,9 @@ SIGNATURES = {
                                             _sz, _vp]),
     "dvf_area_pyramid": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "dvf_area_downsample": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "dvf_reg_workspace_bytes": (_sz, [C.POINTER(dvf_reg_level), _i32]),
+    "dvf_smooth_loss": (C.c_int, [C.POINTER(dvf_reg_level), _i32, _vp, _vp, _sz, _vp]),
+    "dvf_explainability_loss": (C.c_int, [C.POINTER(dvf_reg_level), _i32, _vp, _vp, _sz, _vp]),
     "dvf_selftest_fast_div": (C.c_int, [C.c_uint64, C.c_uint64, _i32, _vp, _vp]),
 }
 

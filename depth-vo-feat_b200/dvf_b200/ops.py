@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import DvfError, PADDING, ROTATION, dvf_desc, dvf_level, dvf_loss_desc, dvf_pose_args
+from ._lib import DvfError, PADDING, ROTATION, dvf_desc, dvf_level, dvf_loss_desc, dvf_pose_args, dvf_reg_level
 
 _WS = {}
 
@@ -405,3 +405,58 @@ def fused_photo_loss(tgt_levels, src_levels, depth_levels, pose, K, Kinv, expl_l
     if cfg.has_expl:
         flat += list(expl_levels)
     return FusedPhotoLoss.apply(cfg, pose, K, Kinv, *flat)
+
+
+# ------------------------------------------------------------------------------------------------
+# regularisers: smooth_loss / explainability_loss (all scales in one launch, value + gradient)
+# ------------------------------------------------------------------------------------------------
+class RegLoss(torch.autograd.Function):
+    """kind = 'smooth' (loss_functions.py:23-41) or 'explainability' (loss_functions_sfm.py:49-56).
+    weights[l] multiplies the l-th map's term; maps are [B,C,h,w] (or [B,h,w]) fp32 CUDA tensors."""
+
+    @staticmethod
+    def forward(ctx, kind, weights, *maps):
+        lib = _lib.load()
+        xs = [_req(m, "map") for m in maps]
+        L = len(xs)
+        if L == 0 or L > _lib.DVF_MAX_LEVELS:
+            raise DvfError(f"1..{_lib.DVF_MAX_LEVELS} maps per call")
+        dev = xs[0].device
+        levels = (dvf_reg_level * L)()
+        grads = []
+        for l, x in enumerate(xs):
+            if x.dim() < 2:
+                raise AssertionError("maps must have at least 2 dimensions")
+            h, w = x.shape[-2], x.shape[-1]
+            n = x.numel() // (h * w)
+            g = torch.empty_like(x) if ctx.needs_input_grad[2 + l] else None
+            grads.append(g)
+            levels[l] = dvf_reg_level(x.data_ptr(), _ptr(g), n, h, w, float(weights[l]))
+        out = torch.empty(1, device=dev, dtype=torch.float32)
+        nbytes = lib.dvf_reg_workspace_bytes(levels, L)
+        ws = workspace(nbytes, dev, ("reg", kind) + tuple(tuple(x.shape) for x in xs))
+        fn = lib.dvf_smooth_loss if kind == "smooth" else lib.dvf_explainability_loss
+        _lib.check(fn(levels, L, _ptr(out), _ptr(ws), ws.numel(), _stream()), "dvf_" + kind + "_loss")
+        ctx.unit_grads = grads
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g_out):
+        grads = ctx.unit_grads
+        ctx.unit_grads = None
+        _scale_inplace(grads, g_out)
+        return (None, None) + tuple(grads)
+
+
+def smooth_loss(maps, scale_factor=1):
+    maps = list(maps) if type(maps) in (tuple, list) else [maps]
+    weights, w = [], 1.0
+    for _ in maps:
+        weights.append(w)
+        w /= scale_factor
+    return RegLoss.apply("smooth", weights, *maps)
+
+
+def explainability_loss(masks):
+    masks = list(masks) if type(masks) in (tuple, list) else [masks]
+    return RegLoss.apply("explainability", [1.0] * len(masks), *masks)

@@ -2,7 +2,7 @@
 
 photometric_reconstruction_loss runs as ONE fused CUDA launch (csrc/dvf_loss.cu) that warps both
 source views, applies the value-based validity masks and produces the loss together with its
-gradients; smooth_loss keeps the reference formula.  CUDA tensors only.
+gradients; smooth_loss is one fused launch over all scales.  CUDA tensors only.
 """
 from __future__ import division
 
@@ -23,19 +23,9 @@ def photometric_reconstruction_loss(img_R2, img_R1, img_L2, depth, T_2to1, T_R2L
 
 
 def smooth_loss(pred_map, scale_factor=1):
-    """loss_functions.py:23-41: second-order smoothness, sum over scales with weight /= scale_factor."""
-    maps = pred_map if type(pred_map) in (tuple, list) else [pred_map]
-    total, weight = 0, 1.
-    for m in maps:
-        dx = m[:, :, :, 1:] - m[:, :, :, :-1]
-        dy = m[:, :, 1:] - m[:, :, :-1]
-        dxx = dx[:, :, :, 1:] - dx[:, :, :, :-1]
-        dxy = dx[:, :, 1:] - dx[:, :, :-1]
-        dyx = dy[:, :, :, 1:] - dy[:, :, :, :-1]
-        dyy = dy[:, :, 1:] - dy[:, :, :-1]
-        total += (dxx.abs().mean() + dxy.abs().mean() + dyx.abs().mean() + dyy.abs().mean()) * weight
-        weight /= scale_factor
-    return total
+    """loss_functions.py:23-41: second-order smoothness, sum over scales with weight /= scale_factor.
+    One fused CUDA launch for all scales (value + gradient, csrc/dvf_reg.cu)."""
+    return _ops.smooth_loss(pred_map, scale_factor)
 
 
 def inverse_warp(img, depth, pose, intrinsics, intrinsics_inv, rotation_mode='euler', padding_mode='zeros'):

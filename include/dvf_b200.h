@@ -183,6 +183,26 @@ int dvf_area_pyramid(const float* img /*[BC,H,W]*/, int32_t BC, int32_t H, int32
 int dvf_area_downsample(const float* img /*[BC,H,W]*/, int32_t BC, int32_t H, int32_t W,
                         int32_t h, int32_t w, float* out /*[BC,h,w]*/, void* stream);
 
+/* ---- regularisers next to the path -----------------------
+ * smooth_loss (loss_functions.py:23-41, loss_functions_sfm.py:59-77) and explainability_loss
+ * (loss_functions_sfm.py:49-56), every scale in ONE launch, value and gradient together.
+ *   x      [B,H,W] fp32 (maps with several channels: fold the channels into B)
+ *   g      same shape, written: d(out)/dx for upstream 1 (nullable)
+ *   weight factor of this level in the sum (smooth_loss: 1/scale_factor^level; explainability: 1)
+ *   out    device float[1]: sum_l weight_l * loss_l                                    */
+typedef struct dvf_reg_level {
+  const float* x;
+  float* g;
+  int32_t B, H, W;
+  float weight;
+} dvf_reg_level;
+
+size_t dvf_reg_workspace_bytes(const dvf_reg_level* levels, int32_t n_levels);
+int dvf_smooth_loss(const dvf_reg_level* levels, int32_t n_levels, float* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int dvf_explainability_loss(const dvf_reg_level* levels, int32_t n_levels, float* out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* ---- diagnostics -----------------------------------------------------------
  * Compares the shared-reciprocal IEEE division of the coordinate chain with
  * __fdiv_rn on n pseudo-random operand pairs (mode 0: float divisors, mode 1:

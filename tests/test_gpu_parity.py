@@ -449,3 +449,38 @@ def test_feature_loss_channels_last_vs_oracle(ops, oracle, syn, dtype, C, V, wit
                      what=f"gpose{v}")
     if with_expl:
         assert_close(npy(t_expl.grad), r["gexpl"], tol=tol_geo, what="gexpl")
+
+
+def test_regularisers_vs_oracle(ops, oracle, syn):
+    """smooth_loss / explainability_loss, all scales in one launch, against the oracle (value and gradient)."""
+    import loss_functions as lf
+    import loss_functions_sfm as sfm
+    B, H, W = 3, 64, 208
+    maps = [syn.depth(B, H >> s, W >> s, 200 + s).unsqueeze(1) for s in range(4)]
+    t = [m.cuda().requires_grad_(True) for m in maps]
+    val = lf.smooth_loss(t, 2.0)
+    (3.0 * val).backward()
+    ref, w = 0.0, 1.0
+    for m, tm in zip(maps, t):
+        v, g = oracle.smooth_loss_one(m[:, 0].numpy(), need_grad=True)
+        ref += v * w
+        assert_close(npy(tm.grad[:, 0]), 3.0 * w * g, what="smooth grad")
+        w /= 2.0
+    assert abs(val.item() - ref) <= RTOL_F32 * ref
+    masks = [syn.explainability(B, 2, H >> s, W >> s, 210 + s) for s in range(3)]
+    tm = [m.cuda().requires_grad_(True) for m in masks]
+    val = sfm.explainability_loss(tm)
+    val.backward()
+    ref = 0.0
+    for m, x in zip(masks, tm):
+        v, g = oracle.explainability_loss_one(m.numpy(), need_grad=True)
+        ref += v
+        assert_close(npy(x.grad), g, what="explainability grad")
+    assert abs(val.item() - ref) <= RTOL_F32 * ref
+    # ragged / degenerate sizes
+    small = torch.rand(2, 1, 2, 5).cuda().requires_grad_(True)
+    v = lf.smooth_loss(small)
+    ov, og = oracle.smooth_loss_one(small.detach().cpu().numpy()[:, 0], need_grad=True)
+    v.backward()
+    assert abs(v.item() - ov) <= 1e-5 * max(ov, 1e-6)
+    assert_close(npy(small.grad[:, 0]), og, what="small smooth grad")

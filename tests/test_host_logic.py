@@ -70,21 +70,15 @@ def test_cpu_tensors_fail_loudly():
         iw.pose_vec2mat(pose)
 
 
-def test_smooth_and_explainability_helpers_on_cpu():
-    # these two are plain tensor algebra next to the CUDA path; check the formulas
+def test_regularisers_refuse_cpu_tensors():
+    from dvf_b200 import DvfError
     import loss_functions as lf
     import loss_functions_sfm as sfm
-    from oracle import cpu_oracle as O
-    g = torch.Generator().manual_seed(0)
-    maps = [torch.rand(2, 1, 16 >> s, 24 >> s, generator=g) + 0.5 for s in range(3)]
-    val = lf.smooth_loss(maps, 2.0)
-    ref, w = 0.0, 1.0
-    for m in maps:
-        ref += O.smooth_loss_one(m[:, 0].numpy()) * w
-        w /= 2.0
-    assert abs(float(val) - ref) < 1e-5 * ref
-    m = torch.rand(2, 2, 8, 8, generator=g) * 0.9 + 0.05
-    assert abs(float(sfm.explainability_loss([m])) - O.explainability_loss_one(m.numpy())) < 1e-6
+    m = torch.rand(2, 1, 8, 8) + 0.5
+    with pytest.raises(DvfError, match="no CPU fallback"):
+        lf.smooth_loss([m], 2.0)
+    with pytest.raises(DvfError, match="no CPU fallback"):
+        sfm.explainability_loss([m * 0.5])
 
 
 def test_product_never_imports_the_oracle():
