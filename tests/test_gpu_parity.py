@@ -484,3 +484,66 @@ def test_regularisers_vs_oracle(ops, oracle, syn):
     v.backward()
     assert abs(v.item() - ov) <= 1e-5 * max(ov, 1e-6)
     assert_close(npy(small.grad[:, 0]), og, what="small smooth grad")
+
+
+@pytest.mark.parametrize("B,H,W,V,with_expl", [(2, 17, 23, 2, True), (1, 2, 3, 1, False), (3, 40, 52, 1, False), (1, 128, 416, 4, True)])
+def test_fused_loss_c3_ragged_shapes_vs_oracle(ops, oracle, syn, B, H, W, V, with_expl):
+    """image kernel (C=3) on sizes that exercise the non-bulk-copy path (H*W % 4 != 0), partial last chunks,
+    several views and masks; the oracle is fed the GPU's own P so the per-pixel path is held to 1e-5."""
+    imgs = syn.images(B, 3, H, W, 31, n=V + 1, smooth=min(H, W) > 9)
+    depth = syn.depth(B, H, W, 32, smooth=min(H, W) > 17)
+    kinds = ["kitti", "stereo", "tiny", "large"]
+    pose = torch.stack([syn.pose(B, kinds[v], 33 + v) for v in range(V)], 1)
+    K, Kinv = syn.intrinsics(B, H, W)
+    expl = syn.explainability(B, V, H, W, 39) if with_expl else None
+    t_depth = depth.cuda().requires_grad_(True)
+    t_pose = pose.cuda().requires_grad_(True)
+    t_expl = None if expl is None else expl.cuda().requires_grad_(True)
+    loss, terms = ops.fused_photo_loss([imgs[0].cuda()], [[m.cuda() for m in imgs[1:]]], [t_depth], t_pose, K.cuda(), Kinv.cuda(),
+                                       expl_levels=None if expl is None else [t_expl])
+    loss.backward()
+    _, P_gpu, _ = ops.pose_proj_fwd(t_pose.detach().reshape(B * V, 6), K.cuda(), None, V, "euler", [1.0])
+    Pn = npy(P_gpu[0]).reshape(B, V, 3, 4)
+    r = oracle.photo_loss_P(imgs[0].numpy(), [m.numpy() for m in imgs[1:]], depth.numpy(), Pn, Kinv.numpy(),
+                            expl=None if expl is None else expl.numpy())
+    assert_close(npy(terms), r["terms"], what="terms")
+    assert np.array_equal(npy(t_depth.grad), r["gdepth"]), "depth gradient is bit-identical to the reference sequence"
+    for v in range(V):
+        assert_close(npy(t_pose.grad[:, v]), oracle.pose_bwd(r["gP"][:, v], K.numpy(), pose[:, v].numpy()), what=f"gpose{v}")
+    if with_expl:
+        assert np.array_equal(npy(t_expl.grad), r["gexpl"])
+
+
+def test_fused_loss_forward_only_and_nan_inputs(ops, oracle, syn):
+    """no_grad mode runs the loss-only kernel; NaN / huge depths take the exact cold path and propagate like the reference."""
+    B, H, W = 2, 24, 80
+    d = syn.stereo_temporal_batch(B, H, W, seed=55)
+    pose = torch.stack([d["T_2to1"], d["T_R2L"]], 1).cuda()
+    depth = d["depth"].clone()
+    with torch.no_grad():
+        loss, terms = ops.fused_photo_loss([d["img_R2"].cuda()], [[d["img_R1"].cuda(), d["img_L2"].cuda()]], [depth.cuda()], pose,
+                                           d["intrinsics"].cuda(), d["intrinsics_inv"].cuda())
+    _, P_gpu, _ = ops.pose_proj_fwd(pose.reshape(B * 2, 6), d["intrinsics"].cuda(), None, 2, "euler", [1.0])
+    Pn = npy(P_gpu[0]).reshape(B, 2, 3, 4)
+    r = oracle.photo_loss_P(d["img_R2"].numpy(), [d["img_R1"].numpy(), d["img_L2"].numpy()], depth.numpy(), Pn,
+                            d["intrinsics_inv"].numpy())
+    assert_close(npy(terms), r["terms"], what="terms (forward only)")
+    # huge (but finite) depths force the __fdiv_rn path on those pixels: results must still match the oracle exactly
+    depth2 = depth.clone()
+    depth2[0, 3, 5] = 3.0e12
+    depth2[1, 7, 9] = 1.0e20
+    t_depth = depth2.cuda().requires_grad_(True)
+    loss, terms = ops.fused_photo_loss([d["img_R2"].cuda()], [[d["img_R1"].cuda(), d["img_L2"].cuda()]], [t_depth], pose,
+                                       d["intrinsics"].cuda(), d["intrinsics_inv"].cuda())
+    loss.backward()
+    r2 = oracle.photo_loss_P(d["img_R2"].numpy(), [d["img_R1"].numpy(), d["img_L2"].numpy()], depth2.numpy(), Pn,
+                             d["intrinsics_inv"].numpy())
+    assert_close(npy(terms), r2["terms"], what="terms (huge depths)")
+    assert np.array_equal(npy(t_depth.grad), r2["gdepth"])
+    # NaN depth: the loss becomes NaN, as in the reference
+    depth3 = depth.clone()
+    depth3[0, 0, 0] = float("nan")
+    with torch.no_grad():
+        loss3, _ = ops.fused_photo_loss([d["img_R2"].cuda()], [[d["img_R1"].cuda(), d["img_L2"].cuda()]], [depth3.cuda()], pose,
+                                        d["intrinsics"].cuda(), d["intrinsics_inv"].cuda())
+    assert torch.isnan(loss3)
