@@ -25,7 +25,6 @@ struct Plan {
   size_t bytes;
 };
 
-// pixels per thread per iteration of the kernel that will run (must match dvf_loss_inst_*.cu)
 static bool uses_c3_kernel(const dvf_loss_desc* d, const dvf_level* levels) {
   if (d->C != 3 || d->layout != DVF_NCHW || d->dtype != DVF_F32) return false;
   for (int l = 0; l < d->n_levels; ++l) {   // the register-resident image kernel has no scatter / d-target outputs
@@ -34,9 +33,6 @@ static bool uses_c3_kernel(const dvf_loss_desc* d, const dvf_level* levels) {
       if (levels[l].gsrc[v]) return false;
   }
   return true;
-}
-static int plan_ppt(const dvf_loss_desc* d, const dvf_level* levels) {
-  return 2;   // both kernels consume kLossThreads*2 pixels per iteration
 }
 
 static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) {
@@ -50,7 +46,7 @@ static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) 
     total_px += (long long)levels[l].H * levels[l].W * d->B;
   }
   // aim for ~6 CTAs per SM over the whole launch (4 resident): fixed per-CTA cost vs tail balance
-  const long long chunk = (long long)kLossThreads * plan_ppt(d, levels);
+  const long long chunk = kPlanUnit;
   const long long want_blocks = 6ll * num_sms();   // measured flat between 4 and 16 CTAs per SM (profiles/r1_summary.md)
   int iters = (int)(total_px / (chunk * want_blocks));
   if (iters < 1) iters = 1;
@@ -173,6 +169,7 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     t.block_begin = pl.block_begin[l];
     t.blocks_per_image = pl.blocks_per_image[l];
     t.iters = pl.iters[l];
+    t.px_per_cta = pl.iters[l] * kPlanUnit;
     t.partials = reinterpret_cast<float*>(ws + pl.off_partials[l]);
     t.img_terms = reinterpret_cast<double*>(ws + pl.off_terms[l]);
     t.img_counter = reinterpret_cast<unsigned*>(ws + pl.off_cnt[l]);

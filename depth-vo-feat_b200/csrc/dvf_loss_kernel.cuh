@@ -4,13 +4,11 @@
 // One launch covers every pyramid level and every source view of a loss call:
 //   * a CTA owns a contiguous run of target pixels of ONE image of ONE level, so the per-image
 //     projection P and K^-1 are CTA-uniform (kept in shared memory, broadcast reads);
-//   * each thread walks kPPT pixels per iteration with stride = CTA width => every depth / target
-//     load and every depth-gradient store is a fully coalesced 128 B line per warp; the loads of the
-//     NEXT iteration are issued before the current one is processed (software prefetch);
+//   * each thread owns adjacent pixels of the run, so every depth / target load and depth-gradient store of a
+//     warp is contiguous; in the image kernel these streaming inputs arrive through a TMA-filled ring;
 //   * per pixel the depth / target values are read once and shared by all V views; the 4 bilinear
 //     taps per channel are read-only gathers (neighbouring lanes hit neighbouring texels; L1 absorbs
-//     the x0/x1 and y0/y1 reuse); the gathers of all kPPT pixels are issued back to back before any
-//     is consumed;
+//     the x0/x1 and y0/y1 reuse);
 //   * the hot path is branch-free straight-line code; pixels whose operands leave the range in which
 //     the shared-reciprocal divisions are exact (|q| > 2^100, NaN) are redone by a cold out-of-line
 //     routine using __fdiv_rn;
@@ -30,7 +28,6 @@
 namespace dvf {
 
 constexpr int kLossThreads = 128;
-constexpr int kPPT = 2;  // pixels per thread per iteration (generic-C kernel; plan granularity)
 
 struct LevelDev {
   int H, W, HW;
@@ -52,6 +49,7 @@ struct LevelDev {
   float* gtgt;
   float* gP;
   int block_begin, blocks_per_image, iters;
+  int px_per_cta;         // contiguous target pixels owned by one CTA (multiple of kPlanUnit)
   float* partials;        // [B*blocks_per_image][V][kRedSlots]
   double* img_terms;      // [B][V]
   unsigned* img_counter;  // [B]   zero between launches
@@ -344,8 +342,8 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3_kernel
   // coordinate chain stays below 2^100 => the shared-reciprocal divisions are exact
   const float depth_max = mats_ok ? 1073741824.0f : -1.0f;
 
-  const int px_end = min((chunk + 1) * (kLossThreads * lv.iters), HW);
-  for (int idx = chunk * (kLossThreads * lv.iters) + tid; idx < px_end; idx += kLossThreads) {
+  const int px_end = min((chunk + 1) * lv.px_per_cta, HW);
+  for (int idx = chunk * lv.px_per_cta + tid; idx < px_end; idx += kLossThreads) {
     const float dep = ld_stream(depth_b + idx);
     const float tg0 = ld_stream(tgt0 + idx), tg1 = ld_stream(tgt1 + idx), tg2 = ld_stream(tgt2 + idx);
     Cam cam;
@@ -429,17 +427,25 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3_kernel
 // kernel is otherwise limited by how many loads its warps can have outstanding.  Requires HW % 4 == 0 and
 // 16-byte aligned tensors (checked on the host); otherwise the same kernel runs with plain loads.
 // ================================================================================================
-constexpr int kChunk = 2 * kLossThreads;   // pixels per chunk (one pair per thread)
+constexpr int kPlanUnit = 512;   // granularity (pixels) of the host's work split; multiple of every kernel's chunk
 constexpr int kStages = 4;
 
 template <int kV, bool kZeros, bool kExpl, bool kGrad, bool kTma, int kMinBlocks = 4>
 __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kernel(const __grid_constant__ LossParams prm) {
   constexpr int kC = 3;
   constexpr int kPlanes = 1 + kC + (kExpl ? kV : 0);   // streamed planes per chunk
+  // pixel pairs per thread between two ring hand-overs: 2 halves the CTA barriers; with masks the ring would get
+  // too shallow (measured: 71 vs 75 us without masks, 151 vs 145 us with masks at V=2)
+  constexpr int kPairsPerChunk = kPlanes <= 4 ? 2 : 1;
+  constexpr int kChunk = 2 * kLossThreads * kPairsPerChunk;    // pixels per chunk
+  static_assert(kPlanUnit % kChunk == 0, "plan unit must be a multiple of the chunk");
+  // ring depth: as deep as 40 KB of static shared memory allow (4 CTAs per SM stay resident), at least 2
+  constexpr int kStagesFit = 40000 / (kPlanes * kChunk * 4);
+  constexpr int kSt = kStagesFit >= kStages ? kStages : (kStagesFit < 2 ? 2 : kStagesFit);
   __shared__ __align__(16) float s_P[kV][12];
   __shared__ __align__(16) float s_M[12];
-  __shared__ __align__(128) float s_ring[kTma ? kStages : 1][kTma ? kPlanes : 1][kTma ? kChunk : 4];
-  __shared__ __align__(8) uint64_t s_full[kStages];
+  __shared__ __align__(128) float s_ring[kTma ? kSt : 1][kTma ? kPlanes : 1][kTma ? kChunk : 4];
+  __shared__ __align__(8) uint64_t s_full[kSt];
 
   int l = 0;
   while (l + 1 < prm.n_levels && (int)blockIdx.x >= prm.lv[l + 1].block_begin) ++l;
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
 
   if (kTma && tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
+    for (int s = 0; s < kSt; ++s) mbar_init(&s_full[s], 1);
     mbar_fence_init();
   }
 
@@ -479,16 +485,16 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
 #pragma unroll
   for (int v = 0; v < kV; ++v) src_b[v] = lv.src[v] + (size_t)b * kC * HW;
 
-  // this CTA owns pixels [px_begin, px_end) of image b, in chunks of kChunk (plan granularity 2*kLossThreads)
-  const int px_begin = chunk * (kChunk * lv.iters);
-  const int px_end = min(px_begin + kChunk * lv.iters, HW);
+  // this CTA owns pixels [px_begin, px_end) of image b (host plan), walked in chunks of kChunk
+  const int px_begin = chunk * lv.px_per_cta;
+  const int px_end = min(px_begin + lv.px_per_cta, HW);
   const int n_chunks = (px_end - px_begin + kChunk - 1) / kChunk;
 
   // producer (thread 0): bulk copies of chunk k into ring stage k % kStages + L2 prefetch of the source rows
   auto issue = [&](int k) {
     const int start = px_begin + k * kChunk;
     const uint32_t bytes = (uint32_t)(min(kChunk, px_end - start) * 4);   // multiple of 16 (HW % 4 == 0)
-    const int st = k % kStages;
+    const int st = k % kSt;
     mbar_expect_tx(&s_full[st], bytes * kPlanes);
     bulk_g2s(&s_ring[st][0][0], depth_b + start, bytes, &s_full[st]);
 #pragma unroll
@@ -512,7 +518,7 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
     }
   };
   if (kTma && tid == 0) {
-    for (int k = 0; k < min(kStages, n_chunks); ++k) issue(k);
+    for (int k = 0; k < min(kSt, n_chunks); ++k) issue(k);
   }
 
   // projection matrices of this image (overlaps with the bulk copies just issued)
@@ -535,21 +541,24 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   // one chunk; kTail = the chunk may contain lanes past the end of the run (only the last chunk can)
   auto do_chunk = [&](int k, auto tail_tag) {
     constexpr bool kTail = decltype(tail_tag)::value;
-    const int idxA = px_begin + k * kChunk + 2 * tid;
+    if (kTma) mbar_wait(&s_full[k % kSt], (uint32_t)(k / kSt) & 1u);
+#pragma unroll 1
+    for (int h = 0; h < kPairsPerChunk; ++h) {
+    const int slot = h * (2 * kLossThreads) + 2 * tid;          // my pair inside the chunk
+    const int idxA = px_begin + k * kChunk + slot;
     const int idxB = idxA + 1;
     const bool liveA = !kTail || idxA < px_end, liveB = !kTail || idxB < px_end;
     f2 dep, tg0, tg1, tg2;
     f2 exv[kExpl ? kV : 1];
     if (kTma) {
-      const int st = k % kStages;
-      mbar_wait(&s_full[st], (uint32_t)(k / kStages) & 1u);
-      dep = *reinterpret_cast<const f2*>(&s_ring[st][0][2 * tid]);
-      tg0 = *reinterpret_cast<const f2*>(&s_ring[st][1][2 * tid]);
-      tg1 = *reinterpret_cast<const f2*>(&s_ring[st][2][2 * tid]);
-      tg2 = *reinterpret_cast<const f2*>(&s_ring[st][3][2 * tid]);
+      const int st = k % kSt;
+      dep = *reinterpret_cast<const f2*>(&s_ring[st][0][slot]);
+      tg0 = *reinterpret_cast<const f2*>(&s_ring[st][1][slot]);
+      tg1 = *reinterpret_cast<const f2*>(&s_ring[st][2][slot]);
+      tg2 = *reinterpret_cast<const f2*>(&s_ring[st][3][slot]);
       if (kExpl) {
 #pragma unroll
-        for (int v = 0; v < kV; ++v) exv[v] = *reinterpret_cast<const f2*>(&s_ring[st][1 + kC + v][2 * tid]);
+        for (int v = 0; v < kV; ++v) exv[v] = *reinterpret_cast<const f2*>(&s_ring[st][1 + kC + v][slot]);
       }
     } else {
       const int ia = kTail ? min(idxA, HW - 1) : idxA, ib = kTail ? min(idxB, HW - 1) : idxB;
@@ -716,9 +725,10 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
       if (liveA) st_stream(gp, gd.x);
       if (liveB) st_stream(gp + 1, gd.y);
     }
+    }  // pairs of this chunk
     if (kTma) {
       __syncthreads();   // every thread has consumed ring stage k % kStages
-      if (tid == 0 && k + kStages < n_chunks) issue(k + kStages);
+      if (tid == 0 && k + kSt < n_chunks) issue(k + kSt);
     }
   };
   for (int k = 0; k + 1 < n_chunks; ++k) do_chunk(k, std::false_type{});
@@ -774,10 +784,9 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_cn_kernel(const __
   const float* depth_b = lv.depth + (size_t)b * HW;
   const float* tgt_b = lv.tgt + img_off;
   float* gtgt_b = lv.gtgt ? lv.gtgt + img_off : nullptr;
-  const int n_px = kLossThreads * kPPT * lv.iters;
-  const int px_begin = chunk * n_px + tid;
+  const int px_begin = chunk * lv.px_per_cta + tid;
 
-  for (int q = 0; q < kPPT * lv.iters; ++q) {
+  for (int q = 0; q < lv.px_per_cta / kLossThreads; ++q) {
     const int idx = px_begin + q * kLossThreads;
     const bool live = idx < HW;
     Cam cam;

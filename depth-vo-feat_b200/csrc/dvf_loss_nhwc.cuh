@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
   const float* depth_b = lv.depth + img_px;
   float* gtgt_b = lv.gtgt ? lv.gtgt + img_px * C : nullptr;
   const int px_per_iter = kLossThreads / lpp;
-  const int px_begin = chunk * (kLossThreads * kPPT * lv.iters);
-  const int px_end = min(px_begin + kLossThreads * kPPT * lv.iters, HW);
+  const int px_begin = chunk * lv.px_per_cta;
+  const int px_end = min(px_begin + lv.px_per_cta, HW);
 
   for (int base = px_begin; base < px_end; base += px_per_iter) {
     const int idx = base + tid / lpp;
