@@ -74,6 +74,8 @@ SIGNATURES = {
     "dvf_reg_workspace_bytes": (_sz, [C.POINTER(dvf_reg_level), _i32]),
     "dvf_smooth_loss": (C.c_int, [C.POINTER(dvf_reg_level), _i32, _vp, _vp, _sz, _vp]),
     "dvf_explainability_loss": (C.c_int, [C.POINTER(dvf_reg_level), _i32, _vp, _vp, _sz, _vp]),
+    "dvf_se3_exp_fwd": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "dvf_se3_exp_bwd": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "dvf_selftest_fast_div": (C.c_int, [C.c_uint64, C.c_uint64, _i32, _vp, _vp]),
 }
 

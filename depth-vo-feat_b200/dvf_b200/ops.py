@@ -460,3 +460,33 @@ def smooth_loss(maps, scale_factor=1):
 def explainability_loss(masks):
     masks = list(masks) if type(masks) in (tuple, list) else [masks]
     return RegLoss.apply("explainability", [1.0] * len(masks), *masks)
+
+
+# ------------------------------------------------------------------------------------------------
+# se(3) -> SE(3) exponential map
+# ------------------------------------------------------------------------------------------------
+class SE3Exp(torch.autograd.Function):
+    """SE3_Generator_KITTI (se3_generate.py:7-103): [B,6,1,1] (w,u) -> [B,1,4,4] float64, on the device."""
+
+    @staticmethod
+    def forward(ctx, input):
+        lib = _lib.load()
+        x = _req(input, "input")
+        B = x.shape[0]
+        flat = x.reshape(B, 6)
+        out = torch.empty(B, 1, 4, 4, device=x.device, dtype=torch.float64)
+        _lib.check(lib.dvf_se3_exp_fwd(_ptr(flat), B, _ptr(out), _stream()), "dvf_se3_exp_fwd")
+        ctx.save_for_backward(flat)
+        ctx.in_shape = tuple(input.shape)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        lib = _lib.load()
+        (flat,) = ctx.saved_tensors
+        B = flat.shape[0]
+        g = grad_output.to(torch.float64).contiguous()
+        gin = torch.empty(B, 6, device=flat.device, dtype=torch.float32)
+        _lib.check(lib.dvf_se3_exp_bwd(_ptr(flat), _ptr(g), B, _ptr(gin), _stream()), "dvf_se3_exp_bwd")
+        return gin.reshape(ctx.in_shape)

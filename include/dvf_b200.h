@@ -203,6 +203,13 @@ int dvf_smooth_loss(const dvf_reg_level* levels, int32_t n_levels, float* out, v
 int dvf_explainability_loss(const dvf_reg_level* levels, int32_t n_levels, float* out, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* ---- se(3) -> SE(3) exponential map ------------------------------
+ * Replaces SE3_Generator_KITTI (pytorch_version/se3_generate.py:7-103; copies in model.py:33-131,
+ * fixmodel.py:10-108, caffe/python/pygeometry.py:6-115).  in [B,6] fp32 = (w, u); out [B,4,4] fp64 =
+ * [[R, R u],[0,1]]; backward: gout [B,4,4] fp64 -> gin [B,6] fp32.                          */
+int dvf_se3_exp_fwd(const float* in, int32_t B, double* out, void* stream);
+int dvf_se3_exp_bwd(const float* in, const double* gout, int32_t B, float* gin, void* stream);
+
 /* ---- diagnostics -----------------------------------------------------------
  * Compares the shared-reciprocal IEEE division of the coordinate chain with
  * __fdiv_rn on n pseudo-random operand pairs (mode 0: float divisors, mode 1:

@@ -185,3 +185,19 @@ def explainability_loss_one(mask, need_grad=False):
     g = np.empty_like(mask) if need_grad else None
     val = lib().dvfo_explainability_loss(_p(mask), C.c_size_t(mask.size), _p(g))
     return (val, g) if need_grad else val
+
+
+def se3_exp(vec6):
+    """se3_generate.py forward: [B,6] (w,u) -> [B,4,4] float64."""
+    v = _f32(vec6).reshape(-1, 6)
+    out = np.empty((v.shape[0], 4, 4), np.float64)
+    lib().dvfo_se3_exp_fwd(_p(v), v.shape[0], _p(out))
+    return out
+
+
+def se3_exp_bwd(vec6, gout):
+    v = _f32(vec6).reshape(-1, 6)
+    g = np.ascontiguousarray(gout, dtype=np.float64).reshape(-1, 4, 4)
+    gin = np.empty((v.shape[0], 6), np.float32)
+    lib().dvfo_se3_exp_bwd(_p(v), _p(g), v.shape[0], _p(gin))
+    return gin

@@ -653,3 +653,84 @@ DVFO_API double dvfo_explainability_loss(const float *mask, size_t n, float *gma
   }
   return acc / (double)n;
 }
+
+/* ------------------------------------------------------------------------ */
+/* se(3) -> SE(3) exponential map  (pytorch_version/se3_generate.py:7-103)   */
+/* ------------------------------------------------------------------------ */
+
+/* forward, se3_generate.py:9-54.  in: [B,6] fp32 = (w(3), u(3));  out: [B,4,4] fp64 = [[R, R u],[0,1]].
+ * Mixed precision as in the reference: theta, c1, c2 in fp32 (numpy float32 scalars), the matrix algebra in fp64. */
+static void se3_R(const float *w, double *R, float *theta_out) {
+  double wx[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0}; /* :15-21 */
+  float theta = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);   /* np.linalg.norm on float32 */
+  for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+  if (theta * theta < 1e-12f) {                                     /* :33 */
+    for (int k = 0; k < 9; ++k) R[k] += wx[k];
+  } else {
+    float c1 = sinf(theta) / theta;                                 /* :37 */
+    float sh = sinf(theta / 2);
+    float c2 = 2 * (sh * sh) / (theta * theta);                    /* :38 */
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        double s = 0;
+        for (int k = 0; k < 3; ++k) s += wx[r * 3 + k] * wx[k * 3 + c];
+        R[r * 3 + c] += (double)c1 * wx[r * 3 + c] + (double)c2 * s; /* :42 */
+      }
+  }
+  *theta_out = theta;
+}
+
+DVFO_API void dvfo_se3_exp_fwd(const float *in, int B, double *out) {
+  for (int b = 0; b < B; ++b) {
+    const float *w = in + b * 6, *u = in + b * 6 + 3;
+    double R[9];
+    float th;
+    se3_R(w, R, &th);
+    double *o = out + b * 16;
+    for (int k = 0; k < 16; ++k) o[k] = 0.0;
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) o[r * 4 + c] = R[r * 3 + c];
+      o[r * 4 + 3] = R[r * 3] * (double)u[0] + R[r * 3 + 1] * (double)u[1] + R[r * 3 + 2] * (double)u[2]; /* :46 */
+    }
+    o[15] = 1.0;
+  }
+}
+
+/* backward, se3_generate.py:56-103.  gout: [B,4,4] fp64;  gin: [B,6] fp32. */
+DVFO_API void dvfo_se3_exp_bwd(const float *in, const double *gout, int B, float *gin) {
+  static const double gen[3][9] = {{0, 0, 0, 0, 0, 1, 0, -1, 0}, {0, 0, -1, 0, 0, 0, 1, 0, 0}, {0, 1, 0, -1, 0, 0, 0, 0, 0}}; /* :79-81 */
+  for (int b = 0; b < B; ++b) {
+    const float *w = in + b * 6, *u = in + b * 6 + 3;
+    const double *g = gout + b * 16;
+    double R[9];
+    float th;
+    se3_R(w, R, &th);
+    double wx[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    double dT[3] = {g[3], g[7], g[11]};
+    for (int c = 0; c < 3; ++c) /* dLdut = dLdT @ R  :68 */
+      gin[b * 6 + 3 + c] = (float)(dT[0] * R[c] + dT[1] * R[3 + c] + dT[2] * R[6 + c]);
+    double dR[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) dR[r * 3 + c] = g[r * 4 + c] + dT[r] * (double)u[c]; /* :71-75 */
+    for (int idx = 0; idx < 3; ++idx) {
+      double dRdw[9];
+      if (th * th < 1e-12f) {
+        for (int k = 0; k < 9; ++k) dRdw[k] = gen[idx][k]; /* :97 */
+      } else {
+        /* cross_term = wx @ ((I - R) e_idx) :87 ; cross = skew(cross_term) :88-94 */
+        double col[3], ct[3];
+        for (int r = 0; r < 3; ++r) col[r] = ((r == idx) ? 1.0 : 0.0) - R[r * 3 + idx];
+        for (int r = 0; r < 3; ++r) ct[r] = wx[r * 3] * col[0] + wx[r * 3 + 1] * col[1] + wx[r * 3 + 2] * col[2];
+        double cr[9] = {0, -ct[2], ct[1], ct[2], 0, -ct[0], -ct[1], ct[0], 0};
+        double th2 = (double)(th * th); /* theta[j]**2 is a float32 square */
+        double A[9];
+        for (int k = 0; k < 9; ++k) A[k] = ((double)w[idx] * wx[k] + cr[k]) / th2; /* :99 */
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) dRdw[r * 3 + c] = A[r * 3] * R[c] + A[r * 3 + 1] * R[3 + c] + A[r * 3 + 2] * R[6 + c];
+      }
+      double s = 0;
+      for (int k = 0; k < 9; ++k) s += dR[k] * dRdw[k]; /* :100 */
+      gin[b * 6 + idx] = (float)s;
+    }
+  }
+}

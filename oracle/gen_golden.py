@@ -124,6 +124,30 @@ def case_sfm(mods, name, B, H, W, n_scales, seed, with_mask, rot, pad, old=False
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
+def case_se3(name, B, seed):
+    """se3_generate.SE3_Generator_KITTI hard-codes `.cuda()` (se3_generate.py:52,103); there is no GPU where the
+    fixtures are generated, so Tensor.cuda is made the identity for the duration of the call -- the reference
+    source itself is untouched."""
+    sys.path.insert(0, REF)
+    sys.modules.pop("se3_generate", None)
+    se3 = importlib.import_module("se3_generate")
+    assert os.path.realpath(se3.__file__).startswith(os.path.realpath(REF))
+    g = torch.Generator().manual_seed(seed)
+    vec = torch.randn(B, 6, 1, 1, generator=g) * torch.tensor([0.2, 0.3, 0.1, 1.0, 0.5, 2.0]).view(1, 6, 1, 1)
+    vec[0, :3] = 0.0            # exercises the theta^2 < 1e-12 branch
+    vec[1, :3] *= 1e-4
+    x = vec.clone().requires_grad_(True)
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        out = se3.generate_se3(x)
+        gout = torch.randn(out.shape, generator=g, dtype=torch.float64)
+        out.backward(gout)
+    finally:
+        torch.Tensor.cuda = orig
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kind="se3", vec=_np(vec), out=_np(out), gout=_np(gout), gvec=_np(x.grad))
+
+
 def main():
     warnings.filterwarnings("ignore")
     torch.set_num_threads(1)
@@ -140,6 +164,7 @@ def main():
     case_sfm(mods, "sfm_3scales_mask", 2, 32, 104, 3, seed=9, with_mask=True, rot="euler", pad="zeros")
     case_sfm(mods, "sfm_2scales_nomask_quat_border", 2, 32, 104, 2, seed=10, with_mask=False, rot="quat", pad="border")
     case_sfm(mods, "sfm_old_2scales_mask", 2, 32, 104, 2, seed=11, with_mask=True, rot="euler", pad="zeros", old=True)
+    case_se3("se3_exp", 6, seed=12)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("wrote", sorted(os.listdir(OUT)), f"{tot / 1024:.0f} KiB")
 

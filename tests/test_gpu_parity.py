@@ -547,3 +547,18 @@ def test_fused_loss_forward_only_and_nan_inputs(ops, oracle, syn):
         loss3, _ = ops.fused_photo_loss([d["img_R2"].cuda()], [[d["img_R1"].cuda(), d["img_L2"].cuda()]], [depth3.cuda()], pose,
                                         d["intrinsics"].cuda(), d["intrinsics_inv"].cuda())
     assert torch.isnan(loss3)
+
+
+def test_se3_exp_dropin_golden(ops, oracle):
+    import se3_generate
+    g = golden("se3_exp")
+    x = cu(g["vec"]).requires_grad_(True)
+    out = se3_generate.generate_se3(x)
+    assert out.dtype == torch.float64 and tuple(out.shape) == tuple(g["out"].shape)
+    # theta, c1, c2 are fp32 in the reference; CUDA sinf vs numpy's sin may differ in the last place
+    assert np.abs(npy(out) - g["out"]).max() < 5e-7
+    out.backward(cu(g["gout"]))
+    assert_close(npy(x.grad), g["gvec"], tol=1e-5, what="se3 grad")
+    big = np.random.default_rng(3).standard_normal((257, 6, 1, 1)).astype(np.float32)
+    o2 = se3_generate.generate_se3(cu(big))
+    assert np.abs(npy(o2)[:, 0] - oracle.se3_exp(big)).max() < 5e-6

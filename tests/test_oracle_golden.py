@@ -91,3 +91,12 @@ def test_smooth_and_explainability_match_closed_form(oracle):
     assert abs(fd - grad[k]) < 5e-3
     m = rng.random((2, 2, 5, 7), dtype=np.float32) * 0.98 + 0.01
     assert abs(oracle.explainability_loss_one(m) - float(-np.log(m.astype(np.float64)).mean())) < 1e-6
+
+
+def test_se3_exp_golden(oracle):
+    """SE(3) exponential map (se3_generate.py) vs the reference run with Tensor.cuda patched to identity."""
+    g = golden("se3_exp")
+    out = oracle.se3_exp(g["vec"])
+    assert np.abs(out - g["out"][:, 0]).max() < 1e-12
+    gin = oracle.se3_exp_bwd(g["vec"], g["gout"])
+    assert_close(gin, g["gvec"].reshape(-1, 6), tol=1e-6, what="se3 grad")
