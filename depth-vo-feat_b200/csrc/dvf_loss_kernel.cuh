@@ -284,141 +284,11 @@ __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], c
 }
 
 // ================================================================================================
-// C == 3 (images): everything of a pixel lives in registers.  No scatter / target-gradient outputs
-// here (requests for those go through the generic kernel below).
-//   kExpl  explainability weights present      kGrad  produce gradients (false: loss only)
-// One pixel per thread per iteration; latency is hidden by occupancy (>= 16 warps / SM), addresses
-// are per-image base pointers + 32-bit offsets.
-// ================================================================================================
-template <int kV, bool kZeros, bool kExpl, bool kGrad, int kMinBlocks = 4>
-__global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3_kernel(const __grid_constant__ LossParams prm) {
-  constexpr int kC = 3;
-  __shared__ __align__(16) float s_P[kV][12];
-  __shared__ __align__(16) float s_M[12];
-
-  int l = 0;
-  while (l + 1 < prm.n_levels && (int)blockIdx.x >= prm.lv[l + 1].block_begin) ++l;
-  const LevelDev& lv = prm.lv[l];
-  const int rel = (int)blockIdx.x - lv.block_begin;
-  const int b = rel / lv.blocks_per_image;
-  const int chunk = rel - b * lv.blocks_per_image;
-  const int tid = threadIdx.x;
-  const int H = lv.H, W = lv.W, HW = lv.HW;
-  const Geo geo = lv.geo;
-  const FastDiv divW = lv.divW;
-  const float inv_n = lv.inv_n;
-
-  load_matrices<kV>(prm, lv, b, s_P, s_M);
-  __syncthreads();
-
-  float acc[kV][kRedSlots];
-#pragma unroll
-  for (int v = 0; v < kV; ++v)
-#pragma unroll
-    for (int k = 0; k < kRedSlots; ++k) acc[v][k] = 0.0f;
-
-  // per-image base pointers; everything below indexes them with 32-bit offsets (3*HW < 2^31)
-  const float* const depth_b = lv.depth + (size_t)b * HW;
-  const float* const tgt0 = lv.tgt + (size_t)b * kC * HW;
-  const float* const tgt1 = tgt0 + HW;
-  const float* const tgt2 = tgt1 + HW;
-  float* const gdepth_b = lv.gdepth + (size_t)b * HW;   // only dereferenced when lv.gdepth != nullptr
-  const bool want_gdepth = lv.gdepth != nullptr;
-  const float* const expl_b = kExpl ? lv.expl + (size_t)b * lv.expl_bstride : nullptr;
-  float* const gexpl_b = (kExpl && lv.gexpl) ? lv.gexpl + (size_t)b * kV * HW : nullptr;
-  // the exact (cold) path is forced when the per-image matrices are not comfortably finite
-  bool mats_ok = lv.allow_fast != 0;
-  float M[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    M[k] = s_M[k];
-    mats_ok = mats_ok && (fabsf(M[k]) <= 1048576.0f /*2^20*/);
-  }
-#pragma unroll
-  for (int v = 0; v < kV; ++v)
-#pragma unroll
-    for (int k = 0; k < 12; ++k) mats_ok = mats_ok && (fabsf(s_P[v][k]) <= 1073741824.0f /*2^30*/);
-  // with |P| <= 2^30, |Kinv| <= 2^20, |depth| <= 2^30 and pixel indices < 2^15 every intermediate of the
-  // coordinate chain stays below 2^100 => the shared-reciprocal divisions are exact
-  const float depth_max = mats_ok ? 1073741824.0f : -1.0f;
-
-  const int px_end = min((chunk + 1) * lv.px_per_cta, HW);
-  for (int idx = chunk * lv.px_per_cta + tid; idx < px_end; idx += kLossThreads) {
-    const float dep = ld_stream(depth_b + idx);
-    const float tg0 = ld_stream(tgt0 + idx), tg1 = ld_stream(tgt1 + idx), tg2 = ld_stream(tgt2 + idx);
-    Cam cam;
-    {
-      const int i = (int)fastdiv((uint32_t)idx, divW);
-      pixel_to_cam(M, dep, i, idx - i * W, cam);
-    }
-    const bool fast = fabsf(dep) <= depth_max;   // false for NaN
-    float gd = 0.0f;
-
-#pragma unroll
-    for (int v = 0; v < kV; ++v) {
-      float P[12];
-#pragma unroll
-      for (int k = 0; k < 12; ++k) P[k] = s_P[v][k];
-      const float* const src0 = lv.src[v] + (size_t)b * kC * HW;
-
-      Proj pr;
-      Loc L;
-      project<false, kZeros>(P, cam, geo, pr);
-      if (__builtin_expect(!fast, 0)) pr = project_exact<kZeros>(&s_P[v][0], cam, &lv.geo);
-      locate<kZeros>(pr.xn, pr.yn, H, W, geo, L);
-
-      const int o0 = L.y0 * W + L.x0;          // nw tap, channel 0
-      const int o1 = o0 + HW, o2 = o1 + HW;
-      const float a00 = L.bnw ? __ldg(src0 + o0) : 0.0f, a01 = L.bne ? __ldg(src0 + o0 + 1) : 0.0f;
-      const float a10 = L.bsw ? __ldg(src0 + o0 + W) : 0.0f, a11 = L.bse ? __ldg(src0 + o0 + W + 1) : 0.0f;
-      const float b00 = L.bnw ? __ldg(src0 + o1) : 0.0f, b01 = L.bne ? __ldg(src0 + o1 + 1) : 0.0f;
-      const float b10 = L.bsw ? __ldg(src0 + o1 + W) : 0.0f, b11 = L.bse ? __ldg(src0 + o1 + W + 1) : 0.0f;
-      const float c00 = L.bnw ? __ldg(src0 + o2) : 0.0f, c01 = L.bne ? __ldg(src0 + o2 + 1) : 0.0f;
-      const float c10 = L.bsw ? __ldg(src0 + o2 + W) : 0.0f, c11 = L.bse ? __ldg(src0 + o2 + W + 1) : 0.0f;
-      float ex = 1.0f;
-      if (kExpl) ex = ld_stream(expl_b + v * HW + idx);
-
-      const float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
-      const float w0 = bilerp(a00, a01, a10, a11, wnw, wne, wsw, wse);
-      const float w1 = bilerp(b00, b01, b10, b11, wnw, wne, wsw, wse);
-      const float w2 = bilerp(c00, c01, c10, c11, wnw, wne, wsw, wse);
-      const bool any = (w0 != 0.0f) || (w1 != 0.0f) || (w2 != 0.0f);
-      const float e0 = sub(tg0, w0), e1 = sub(tg1, w1), e2 = sub(tg2, w2);            // tgt - warped
-      const float f0 = kExpl ? mul(e0, ex) : e0, f1 = kExpl ? mul(e1, ex) : e1, f2 = kExpl ? mul(e2, ex) : e2;
-      const float lsum = add(add(fabsf(f0), fabsf(f1)), fabsf(f2));
-      acc[v][12] += any ? lsum : 0.0f;
-      if (kGrad) {
-        const float s0 = signed_unit(f0, inv_n, any), s1 = signed_unit(f1, inv_n, any), s2 = signed_unit(f2, inv_n, any);
-        const float g0 = kExpl ? mul(s0, ex) : s0, g1 = kExpl ? mul(s1, ex) : s1, g2 = kExpl ? mul(s2, ex) : s2;
-        float gx = 0.0f, gy = 0.0f;
-        bilerp_grad(a00, a01, a10, a11, L, -g0, gx, gy);
-        bilerp_grad(b00, b01, b10, b11, L, -g1, gx, gy);
-        bilerp_grad(c00, c01, c10, c11, L, -g2, gx, gy);
-        if (kExpl) {
-          if (gexpl_b) st_stream(gexpl_b + v * HW + idx, add(add(mul(s0, e0), mul(s1, e1)), mul(s2, e2)));
-        }
-        ChainGrad cg;
-        chain_backward<false>(P, cam, pr, L, gx, gy, geo, cg);
-        if (__builtin_expect(!fast, 0)) cg = chain_backward_exact(&s_P[v][0], cam, pr, L, gx, gy, &lv.geo);
-        gd = add(gd, cg.gdepth);
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) acc[v][r * 4 + k] = fmaf(cg.gq[r], cam.cam[k], acc[v][r * 4 + k]);
-          acc[v][r * 4 + 3] += cg.gq[r];
-        }
-      }
-    }  // views
-    if (kGrad && want_gdepth) st_stream(gdepth_b + idx, gd);
-  }  // pixels
-
-  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, rel, b, kC);
-}
-
-// ================================================================================================
-// C == 3, packed: each thread owns TWO horizontally adjacent target pixels and runs the whole
+// C == 3 (images), packed: each thread owns TWO horizontally adjacent target pixels and runs the whole
 // floating-point chain on (pixel A, pixel B) pairs with FFMA2 / FMUL2 / FADD2 (dvf_math2.cuh).
-// Same results bit for bit as the scalar kernel above; ~half the floating-point issue slots.
+// Same results bit for bit as the scalar arithmetic of dvf_math.cuh (used by the other kernels); ~half the
+// floating-point issue slots.  No scatter / target-gradient outputs here (those requests go through the
+// generic kernel below).
 //
 // kTma: the streaming inputs (depth, 3 target planes, explainability weights) of a CTA's run of pixels
 // are contiguous in memory; they are fetched by 1-D bulk asynchronous copies (TMA) into a kStages-deep
@@ -535,7 +405,9 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   for (int v = 0; v < kV; ++v)
 #pragma unroll
     for (int k = 0; k < 12; ++k) mats_ok = mats_ok && (fabsf(s_P[v][k]) <= 1073741824.0f);
-  const float depth_max = mats_ok ? 1073741824.0f : -1.0f;   // see photo_loss_c3_kernel
+  // with |P| <= 2^30, |Kinv| <= 2^20, |depth| <= 2^30 and pixel indices < 2^15 every intermediate of the coordinate
+  // chain stays below 2^100 => the shared-reciprocal divisions are exact; anything else takes the cold exact path
+  const float depth_max = mats_ok ? 1073741824.0f : -1.0f;
 
 
   // one chunk; kTail = the chunk may contain lanes past the end of the run (only the last chunk can)
@@ -615,11 +487,7 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
       }
       locate2<kZeros>(pr.xn, pr.yn, H, W, geo, geo2, L);
 
-#if defined(DVF_EXP_NOGATHER)
-      const int oA = min(idxA, HW - W - 2), oB = min(idxB, HW - W - 2);   // experiment: coalesced instead of gathered taps
-#else
       const int oA = L.y0A * W + L.x0A, oB = L.y0B * W + L.x0B;
-#endif
       const bool nwA = L.nwA && liveA, neA = L.neA && liveA, swA = L.swA && liveA, seA = L.seA && liveA;
       const bool nwB = L.nwB && liveB, neB = L.neB && liveB, swB = L.swB && liveB, seB = L.seB && liveB;
       f2 t00[kC], t01[kC], t10[kC], t11[kC];

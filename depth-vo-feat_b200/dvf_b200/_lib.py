@@ -76,6 +76,13 @@ SIGNATURES = {
     "dvf_explainability_loss": (C.c_int, [C.POINTER(dvf_reg_level), _i32, _vp, _vp, _sz, _vp]),
     "dvf_se3_exp_fwd": (C.c_int, [_vp, _i32, _vp, _vp]),
     "dvf_se3_exp_bwd": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    "dvf_caffe_geo_fwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "dvf_caffe_geo_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "dvf_caffe_pinhole_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "dvf_caffe_pinhole_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "dvf_caffe_warp_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "dvf_caffe_warp_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "dvf_caffe_abs_loss": (C.c_int, [_vp, _vp, C.c_uint64, _i32, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     "dvf_selftest_fast_div": (C.c_int, [C.c_uint64, C.c_uint64, _i32, _vp, _vp]),
 }
 

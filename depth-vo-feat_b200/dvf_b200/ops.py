@@ -490,3 +490,140 @@ class SE3Exp(torch.autograd.Function):
         gin = torch.empty(B, 6, device=flat.device, dtype=torch.float32)
         _lib.check(lib.dvf_se3_exp_bwd(_ptr(flat), _ptr(g), B, _ptr(gin), _stream()), "dvf_se3_exp_bwd")
         return gin.reshape(ctx.in_shape)
+
+
+# ---- Caffe-convention layers (csrc/dvf_caffe.cu) --------------------------------------------------------
+def _k4(cam_intrinsic, N):
+    k = _req(cam_intrinsic, "cam_intrinsic")
+    if k.numel() != N * 4:
+        raise AssertionError(f"wrong size for cam_intrinsic, expected [{N},4,1,1] (fx,fy,cx,cy), got {list(k.size())}")
+    return k.reshape(N, 4)
+
+
+class GeoTransform(torch.autograd.Function):
+    """GeoTransformLayer (caffe/src/caffe/layers/geometry_transformation.cu:10-176; geo_transform.py:6-38):
+    depthmap [N,1,H,W], pose [N,1,4,4] (fp32 or the fp64 SE3Exp output), cam_intrinsic [N,4,1,1] -> points [N,3,H,W]."""
+
+    @staticmethod
+    def forward(ctx, depthmap, pose, cam_intrinsic):
+        lib = _lib.load()
+        d = _req(depthmap, "depthmap", 4)
+        N, one, H, W = d.shape
+        if one != 1:
+            raise AssertionError(f"wrong size for depthmap, expected [N,1,H,W], got {list(d.size())}")
+        if not isinstance(pose, torch.Tensor) or pose.numel() != N * 16:
+            raise AssertionError(f"wrong size for pose, expected [{N},1,4,4]")
+        T = _req(pose.to(torch.float32), "pose").reshape(N, 16)
+        k = _k4(cam_intrinsic, N)
+        pts = torch.empty(N, 3, H, W, device=d.device, dtype=torch.float32)
+        _lib.check(lib.dvf_caffe_geo_fwd(_ptr(d), _ptr(T), _ptr(k), N, H, W, _ptr(pts), _stream()), "dvf_caffe_geo_fwd")
+        ctx.save_for_backward(d, T, k)
+        ctx.meta = (tuple(pose.shape), pose.dtype, tuple(cam_intrinsic.shape))
+        return pts
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gpts):
+        lib = _lib.load()
+        d, T, k = ctx.saved_tensors
+        N, _, H, W = d.shape
+        pose_shape, pose_dtype, k_shape = ctx.meta
+        g = _req(gpts, "grad_points", 4)
+        nd, nT, nK = ctx.needs_input_grad
+        gd = torch.empty_like(d) if nd else None
+        gT = torch.empty(N, 16, device=d.device, dtype=torch.float32) if nT else None
+        gK = torch.empty(N, 4, device=d.device, dtype=torch.float32) if nK else None
+        _lib.check(lib.dvf_caffe_geo_bwd(_ptr(g), _ptr(d), _ptr(T), _ptr(k), N, H, W, _ptr(gd), _ptr(gT), _ptr(gK), _stream()),
+                   "dvf_caffe_geo_bwd")
+        return gd, None if gT is None else gT.reshape(pose_shape).to(pose_dtype), None if gK is None else gK.reshape(k_shape)
+
+
+class PinHoleProject(torch.autograd.Function):
+    """PinHoleLayer (pin_hole_layer.cu:10-146; geo_transform.py:40-59): points [N,3,H,W], cam_intrinsic [N,4,1,1] ->
+    proj_coords [N,2,H,W] in pixels (the layer's `flows` top is silenced in every reference prototxt)."""
+
+    @staticmethod
+    def forward(ctx, transformed_points, cam_intrinsic):
+        lib = _lib.load()
+        p = _req(transformed_points, "transformed_points", 4)
+        N, three, H, W = p.shape
+        if three != 3:
+            raise AssertionError(f"wrong size for transformed_points, expected [N,3,H,W], got {list(p.size())}")
+        k = _k4(cam_intrinsic, N)
+        out = torch.empty(N, 2, H, W, device=p.device, dtype=torch.float32)
+        _lib.check(lib.dvf_caffe_pinhole_fwd(_ptr(p), _ptr(k), N, H, W, _ptr(out), _stream()), "dvf_caffe_pinhole_fwd")
+        ctx.save_for_backward(p, k)
+        ctx.k_shape = tuple(cam_intrinsic.shape)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gcoords):
+        lib = _lib.load()
+        p, k = ctx.saved_tensors
+        N, _, H, W = p.shape
+        g = _req(gcoords, "grad_coords", 4)
+        gp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        gK = torch.empty(N, 4, device=p.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        _lib.check(lib.dvf_caffe_pinhole_bwd(_ptr(g), _ptr(p), _ptr(k), N, H, W, _ptr(gp), _ptr(gK), _stream()),
+                   "dvf_caffe_pinhole_bwd")
+        return gp, None if gK is None else gK.reshape(ctx.k_shape)
+
+
+class PixelWarp(torch.autograd.Function):
+    """InverseWarpingLayer (inverse_warping_layer.cu:10-169; geo_transform.py:76-125): img [N,C,H,W] sampled
+    bilinearly at proj_coords [N,2,H,W] given in PIXELS; taps outside the image contribute zero."""
+
+    @staticmethod
+    def forward(ctx, img, proj_coords):
+        lib = _lib.load()
+        u = _req(img, "img", 4)
+        N, Cc, H, W = u.shape
+        xy = _req(proj_coords, "proj_coords", 4)
+        if tuple(xy.shape) != (N, 2, H, W):
+            raise AssertionError(f"wrong size for proj_coords, expected {[N, 2, H, W]}, got {list(xy.size())}")
+        out = torch.empty_like(u)
+        _lib.check(lib.dvf_caffe_warp_fwd(_ptr(u), _ptr(xy), N, Cc, H, W, _ptr(out), _stream()), "dvf_caffe_warp_fwd")
+        ctx.save_for_backward(u, xy)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        lib = _lib.load()
+        u, xy = ctx.saved_tensors
+        N, Cc, H, W = u.shape
+        g = _req(gout, "grad_output", 4)
+        gu = torch.empty_like(u) if ctx.needs_input_grad[0] else None
+        gxy = torch.empty_like(xy) if ctx.needs_input_grad[1] else None
+        _lib.check(lib.dvf_caffe_warp_bwd(_ptr(g), _ptr(u), _ptr(xy), N, Cc, H, W, _ptr(gu), _ptr(gxy), _stream()),
+                   "dvf_caffe_warp_bwd")
+        return gu, gxy
+
+
+class AbsLoss(torch.autograd.Function):
+    """AbsLossLayer (abs_loss_layer.cu:10-50): sum|a-b| / a.size(0); d/da = +-1/num with sign(0) := -1."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        lib = _lib.load()
+        x, y = _req(a, "a"), _req(b, "b")
+        if x.shape != y.shape:
+            raise AssertionError(f"wrong size for b, expected {list(x.size())}, got {list(y.size())}")
+        loss = torch.empty(1, device=x.device, dtype=torch.float32)
+        ga = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        ws = workspace(8, x.device, ("abs_loss",))
+        _lib.check(lib.dvf_caffe_abs_loss(_ptr(x), _ptr(y), x.numel(), x.shape[0], 1.0, _ptr(loss), _ptr(ga), _ptr(gb), _ptr(ws),
+                                          _stream()), "dvf_caffe_abs_loss")
+        ctx.save_for_backward(*[t for t in (ga, gb) if t is not None])
+        ctx.has = (ga is not None, gb is not None)
+        return loss[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        saved = list(ctx.saved_tensors)
+        ga = saved.pop(0) * g if ctx.has[0] else None
+        gb = saved.pop(0) * g if ctx.has[1] else None
+        return ga, gb

@@ -210,6 +210,25 @@ int dvf_explainability_loss(const dvf_reg_level* levels, int32_t n_levels, float
 int dvf_se3_exp_fwd(const float* in, int32_t B, double* out, void* stream);
 int dvf_se3_exp_bwd(const float* in, const double* gout, int32_t B, float* gin, void* stream);
 
+/* ---- Caffe-convention layers ---------------------------------------
+ * GeoTransform / PinHole / InverseWarping / AbsLoss of caffe/src/caffe/layers/{geometry_transformation,
+ * pin_hole_layer,inverse_warping_layer,abs_loss_layer}.cu (transliterated, non-functional, in
+ * pytorch_version/geo_transform.py:6-125; called from unsupervise_dvo.py:95-122).  Pixel-space sample positions,
+ * K [N,4] = (fx,fy,cx,cy), T [N,16] = row-major 4x4, pts [N,3,H,W], coords [N,2,H,W], images [N,C,H,W], fp32.
+ * Backward entries WRITE their outputs (the small T/K/img accumulators are zeroed inside); any output may be NULL. */
+int dvf_caffe_geo_fwd(const float* depth, const float* T, const float* K, int32_t N, int32_t H, int32_t W, float* pts, void* stream);
+int dvf_caffe_geo_bwd(const float* top_diff, const float* depth, const float* T, const float* K, int32_t N, int32_t H, int32_t W,
+                      float* depth_diff, float* T_diff, float* K_diff, void* stream);
+int dvf_caffe_pinhole_fwd(const float* pts, const float* K, int32_t N, int32_t H, int32_t W, float* coords, void* stream);
+int dvf_caffe_pinhole_bwd(const float* coords_diff, const float* pts, const float* K, int32_t N, int32_t H, int32_t W,
+                          float* pts_diff, float* K_diff, void* stream);
+int dvf_caffe_warp_fwd(const float* img, const float* coords, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream);
+int dvf_caffe_warp_bwd(const float* top_diff, const float* img, const float* coords, int32_t N, int32_t C, int32_t H, int32_t W,
+                       float* img_diff, float* coords_diff, void* stream);
+/* loss[0] = sum|a-b| / num;  ga = weight/num * ((d>0)-(d<=0)), gb = -ga (nullable); workspace: >= 8 bytes, 8-aligned */
+int dvf_caffe_abs_loss(const float* a, const float* b, uint64_t count, int32_t num, float weight, float* loss, float* ga,
+                       float* gb, void* workspace, void* stream);
+
 /* ---- diagnostics -----------------------------------------------------------
  * Compares the shared-reciprocal IEEE division of the coordinate chain with
  * __fdiv_rn on n pseudo-random operand pairs (mode 0: float divisors, mode 1:

@@ -201,3 +201,62 @@ def se3_exp_bwd(vec6, gout):
     gin = np.empty((v.shape[0], 6), np.float32)
     lib().dvfo_se3_exp_bwd(_p(v), _p(g), v.shape[0], _p(gin))
     return gin
+
+
+# ---- Caffe-convention layers (parity unpinned: see dvf_oracle.c) ------------------------------
+def caffe_geo_fwd(depth, T, K):
+    depth, T, K = _f32(depth), _f32(T).reshape(-1, 16), _f32(K).reshape(-1, 4)
+    N, H, W = depth.shape
+    pts = np.empty((N, 3, H, W), np.float32)
+    lib().dvfo_caffe_geo_fwd(_p(depth), _p(T), _p(K), N, H, W, _p(pts))
+    return pts
+
+
+def caffe_geo_bwd(top, depth, T, K):
+    top, depth, T, K = _f32(top), _f32(depth), _f32(T).reshape(-1, 16), _f32(K).reshape(-1, 4)
+    N, H, W = depth.shape
+    dd, dT, dK = np.empty_like(depth), np.empty((N, 16), np.float32), np.empty((N, 4), np.float32)
+    lib().dvfo_caffe_geo_bwd(_p(top), _p(depth), _p(T), _p(K), N, H, W, _p(dd), _p(dT), _p(dK))
+    return dd, dT, dK
+
+
+def caffe_pinhole_fwd(pts, K):
+    pts, K = _f32(pts), _f32(K).reshape(-1, 4)
+    N, _, H, W = pts.shape
+    out = np.empty((N, 2, H, W), np.float32)
+    lib().dvfo_caffe_pinhole_fwd(_p(pts), _p(K), N, H, W, _p(out))
+    return out
+
+
+def caffe_pinhole_bwd(cdiff, pts, K):
+    cdiff, pts, K = _f32(cdiff), _f32(pts), _f32(K).reshape(-1, 4)
+    N, _, H, W = pts.shape
+    dp, dK = np.empty_like(pts), np.empty((N, 4), np.float32)
+    lib().dvfo_caffe_pinhole_bwd(_p(cdiff), _p(pts), _p(K), N, H, W, _p(dp), _p(dK))
+    return dp, dK
+
+
+def caffe_warp_fwd(img, xy):
+    img, xy = _f32(img), _f32(xy)
+    N, Cc, H, W = img.shape
+    out = np.empty_like(img)
+    lib().dvfo_caffe_warp_fwd(_p(img), _p(xy), N, Cc, H, W, _p(out))
+    return out
+
+
+def caffe_warp_bwd(top, img, xy, need_gimg=True):
+    top, img, xy = _f32(top), _f32(img), _f32(xy)
+    N, Cc, H, W = img.shape
+    gi = np.empty_like(img) if need_gimg else None
+    gxy = np.empty_like(xy)
+    lib().dvfo_caffe_warp_bwd(_p(top), _p(img), _p(xy), N, Cc, H, W, _p(gi), _p(gxy))
+    return gi, gxy
+
+
+def caffe_abs_loss(a, b, weight=1.0):
+    a, b = _f32(a), _f32(b)
+    ga, gb = np.empty_like(a), np.empty_like(b)
+    f = lib().dvfo_caffe_abs_loss
+    f.restype = C.c_double
+    val = f(_p(a), _p(b), C.c_size_t(a.size), a.shape[0], C.c_float(weight), _p(ga), _p(gb))
+    return val, ga, gb

@@ -734,3 +734,164 @@ DVFO_API void dvfo_se3_exp_bwd(const float *in, const double *gout, int B, float
     }
   }
 }
+
+/* ------------------------------------------------------------------------ */
+/* Caffe-convention layers: GeoTransform, PinHole,            */
+/* InverseWarping, AbsLoss -- restated from the .cu files in caffe/src/caffe/layers. */
+/* PARITY UNPINNED for this block: BVLC Caffe is not vendored, the layers    */
+/* cannot be built or run here; the restatement follows the kernel sources   */
+/* expression by expression (same C promotion rules: `Z+1e-12` is double).   */
+/* Layouts: depth [N,H,W], T [N,16] (row-major 4x4), K [N,4]=(fx,fy,cx,cy),  */
+/* pts [N,3,H,W], coords [N,2,H,W] in PIXEL units, images [N,C,H,W].         */
+/* ------------------------------------------------------------------------ */
+
+/* GeoTransform forward, geometry_transformation.cu:10-47 */
+DVFO_API void dvfo_caffe_geo_fwd(const float *depth, const float *T, const float *K, int N, int H, int W, float *pts) {
+  for (int n = 0; n < N; ++n)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        const float *t = T + n * 16, *k = K + n * 4;
+        const float fx = k[0], fy = k[1], cx = k[2], cy = k[3];
+        const float d = depth[((size_t)n * H + y) * W + x];
+        const float X = (x - cx) / fx * d, Y = (y - cy) / fy * d;
+        pts[(((size_t)n * 3 + 0) * H + y) * W + x] = t[0] * X + t[1] * Y + t[2] * d + t[3];
+        pts[(((size_t)n * 3 + 1) * H + y) * W + x] = t[4] * X + t[5] * Y + t[6] * d + t[7];
+        pts[(((size_t)n * 3 + 2) * H + y) * W + x] = t[8] * X + t[9] * Y + t[10] * d + t[11];
+      }
+}
+
+/* GeoTransform backward, geometry_transformation.cu:72-176 (atomics replaced by ordered fp64 sums) */
+DVFO_API void dvfo_caffe_geo_bwd(const float *top, const float *depth, const float *T, const float *K, int N, int H, int W,
+                                 float *depth_diff, float *T_diff /*[N,16]*/, float *K_diff /*[N,4]*/) {
+  for (int n = 0; n < N; ++n) {
+    double accT[16] = {0}, accK[4] = {0};
+    const float *t = T + n * 16, *k = K + n * 4;
+    const float fx = k[0], fy = k[1], cx = k[2], cy = k[3];
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        const size_t o = ((size_t)n * H + y) * W + x;
+        const float gx = top[(((size_t)n * 3 + 0) * H + y) * W + x], gy = top[(((size_t)n * 3 + 1) * H + y) * W + x],
+                    gz = top[(((size_t)n * 3 + 2) * H + y) * W + x];
+        const float bX = (x - cx) / fx, bY = (y - cy) / fy, d = depth[o];
+        float dd = 0;
+        dd += gx * (t[0] * bX + t[1] * bY + t[2]);
+        dd += gy * (t[4] * bX + t[5] * bY + t[6]);
+        dd += gz * (t[8] * bX + t[9] * bY + t[10]);
+        depth_diff[o] = dd;
+        const float g3[3] = {gx, gy, gz};
+        for (int r = 0; r < 3; ++r) {
+          accT[r * 4 + 0] += g3[r] * bX * d;
+          accT[r * 4 + 1] += g3[r] * bY * d;
+          accT[r * 4 + 2] += g3[r] * d;
+          accT[r * 4 + 3] += g3[r] * 1.0f;
+        }
+        float sx = 0, sy = 0;
+        sx += gx * t[0]; sx += gy * t[4]; sx += gz * t[8];
+        sy += gx * t[1]; sy += gy * t[5]; sy += gz * t[9];
+        accK[2] += sx * (-d / fx);
+        accK[3] += sy * (-d / fy);
+        accK[0] += sx * (-bX / fx * d);
+        accK[1] += sy * (-bY / fy * d);
+      }
+    for (int q = 0; q < 16; ++q) T_diff[n * 16 + q] = (float)accT[q];
+    for (int q = 0; q < 4; ++q) K_diff[n * 4 + q] = (float)accK[q];
+  }
+}
+
+/* PinHoleProjection forward, pin_hole_layer.cu:10-50 (proj_coords output; the flow output is always silenced) */
+DVFO_API void dvfo_caffe_pinhole_fwd(const float *pts, const float *K, int N, int H, int W, float *coords) {
+  for (int n = 0; n < N; ++n)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        const float *k = K + n * 4;
+        const float fx = k[0], fy = k[1], cx = k[2], cy = k[3];
+        const float X = pts[(((size_t)n * 3 + 0) * H + y) * W + x], Y = pts[(((size_t)n * 3 + 1) * H + y) * W + x],
+                    Z = pts[(((size_t)n * 3 + 2) * H + y) * W + x];
+        coords[(((size_t)n * 2 + 0) * H + y) * W + x] = (float)(fx * X / (Z + 1e-12) + cx);
+        coords[(((size_t)n * 2 + 1) * H + y) * W + x] = (float)(fy * Y / (Z + 1e-12) + cy);
+      }
+}
+
+/* PinHole backward, pin_hole_layer.cu:76-146 with top_flows_diff = 0 */
+DVFO_API void dvfo_caffe_pinhole_bwd(const float *cdiff, const float *pts, const float *K, int N, int H, int W, float *pts_diff,
+                                     float *K_diff) {
+  for (int n = 0; n < N; ++n) {
+    double accK[4] = {0};
+    const float fx = K[n * 4], fy = K[n * 4 + 1];
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        const size_t oX = (((size_t)n * 3 + 0) * H + y) * W + x, oY = (((size_t)n * 3 + 1) * H + y) * W + x,
+                     oZ = (((size_t)n * 3 + 2) * H + y) * W + x;
+        const float gx = cdiff[(((size_t)n * 2 + 0) * H + y) * W + x], gy = cdiff[(((size_t)n * 2 + 1) * H + y) * W + x];
+        const float X = pts[oX], Y = pts[oY], Z = pts[oZ];
+        float v;
+        v = 0; v += (float)(gx * fx / (Z + 1e-12)); pts_diff[oX] = v;
+        v = 0; v += (float)(gy * fy / (Z + 1e-12)); pts_diff[oY] = v;
+        v = 0; v += (float)(-gx * fx * X / (Z * Z + 1e-12)); v += (float)(-gy * fy * Y / (Z * Z + 1e-12)); pts_diff[oZ] = v;
+        accK[2] += gx;
+        accK[3] += gy;
+        accK[0] += (float)(gx * X / (Z + 1e-12));
+        accK[1] += (float)(gy * Y / (Z + 1e-12));
+      }
+    for (int q = 0; q < 4; ++q) K_diff[n * 4 + q] = (float)accK[q];
+  }
+}
+
+/* InverseWarping forward, inverse_warping_layer.cu:10-52 (pixel-space bilinear, per-tap zero outside the image) */
+DVFO_API void dvfo_caffe_warp_fwd(const float *U, const float *xy, int N, int C, int H, int W, float *out) {
+  for (int n = 0; n < N; ++n)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        const float xx = xy[(((size_t)n * 2 + 0) * H + y) * W + x], yy = xy[(((size_t)n * 2 + 1) * H + y) * W + x];
+        const int x1 = (int)floorf(xx), x2 = x1 + 1, y1 = (int)floorf(yy), y2 = y1 + 1;
+        const float wx2 = xx - (float)x1, wx1 = (float)x2 - xx, wy2 = yy - (float)y1, wy1 = (float)y2 - yy;
+        for (int c = 0; c < C; ++c) {
+          const float *pl = U + ((size_t)n * C + c) * H * W;
+          float v = 0;
+          if (x1 >= 0 && x1 <= W - 1 && y1 >= 0 && y1 <= H - 1) v += wx1 * wy1 * pl[x1 + y1 * W];
+          if (x1 >= 0 && x1 <= W - 1 && y2 >= 0 && y2 <= H - 1) v += wx1 * wy2 * pl[x1 + y2 * W];
+          if (x2 >= 0 && x2 <= W - 1 && y1 >= 0 && y1 <= H - 1) v += wx2 * wy1 * pl[x2 + y1 * W];
+          if (x2 >= 0 && x2 <= W - 1 && y2 >= 0 && y2 <= H - 1) v += wx2 * wy2 * pl[x2 + y2 * W];
+          out[((size_t)n * C + c) * H * W + x + y * W] = v;
+        }
+      }
+}
+
+/* InverseWarping backward, inverse_warping_layer.cu:84-169 */
+DVFO_API void dvfo_caffe_warp_bwd(const float *top, const float *U, const float *xy, int N, int C, int H, int W,
+                                  float *U_diff /*nullable, zeroed here*/, float *xy_diff) {
+  if (U_diff) memset(U_diff, 0, sizeof(float) * (size_t)N * C * H * W);
+  for (int n = 0; n < N; ++n)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        const size_t ox = (((size_t)n * 2 + 0) * H + y) * W + x, oy = (((size_t)n * 2 + 1) * H + y) * W + x;
+        const float xx = xy[ox], yy = xy[oy];
+        const int x1 = (int)floorf(xx), x2 = x1 + 1, y1 = (int)floorf(yy), y2 = y1 + 1;
+        const float wx2 = xx - (float)x1, wx1 = (float)x2 - xx, wy2 = yy - (float)y1, wy1 = (float)y2 - yy;
+        float tl = 0, tr = 0, bl = 0, br = 0;
+        for (int c = 0; c < C; ++c) {
+          const size_t off = ((size_t)n * C + c) * H * W;
+          const float g = top[off + (size_t)W * y + x];
+          if (x1 >= 0 && x1 <= W - 1 && y1 >= 0 && y1 <= H - 1) { if (U_diff) U_diff[off + x1 + y1 * W] += g * wx1 * wy1; tl += g * U[off + W * y1 + x1]; }
+          if (x1 >= 0 && x1 <= W - 1 && y2 >= 0 && y2 <= H - 1) { if (U_diff) U_diff[off + x1 + y2 * W] += g * wx1 * wy2; bl += g * U[off + W * y2 + x1]; }
+          if (x2 >= 0 && x2 <= W - 1 && y1 >= 0 && y1 <= H - 1) { if (U_diff) U_diff[off + x2 + y1 * W] += g * wx2 * wy1; tr += g * U[off + W * y1 + x2]; }
+          if (x2 >= 0 && x2 <= W - 1 && y2 >= 0 && y2 <= H - 1) { if (U_diff) U_diff[off + x2 + y2 * W] += g * wx2 * wy2; br += g * U[off + W * y2 + x2]; }
+        }
+        xy_diff[ox] = (tr - tl) * wy1 + (br - bl) * wy2;
+        xy_diff[oy] = (bl - tl) * wx1 + (br - tr) * wx2;
+      }
+}
+
+/* AbsLoss, abs_loss_layer.cu:10-50: loss = sum|a-b| / num ; d/da = alpha * ((d>0) - (d<=0)), alpha = w/num */
+DVFO_API double dvfo_caffe_abs_loss(const float *a, const float *b, size_t count, int num, float weight, float *ga, float *gb) {
+  double s = 0;
+  const float alpha = weight / (float)num;
+  for (size_t i = 0; i < count; ++i) {
+    const float d = a[i] - b[i];
+    s += fabs((double)d);
+    const float sg = (float)((d > 0) - (d <= 0));
+    if (ga) ga[i] = alpha * sg;
+    if (gb) gb[i] = -alpha * sg;
+  }
+  return s / (double)num;
+}

@@ -562,3 +562,102 @@ def test_se3_exp_dropin_golden(ops, oracle):
     big = np.random.default_rng(3).standard_normal((257, 6, 1, 1)).astype(np.float32)
     o2 = se3_generate.generate_se3(cu(big))
     assert np.abs(npy(o2)[:, 0] - oracle.se3_exp(big)).max() < 5e-6
+
+
+# ---- Caffe-convention layers -- oracle is "parity unpinned" for this family --------------------------
+def _caffe_case(N, H, W, C, seed):
+    rng = np.random.default_rng(seed)
+    depth = rng.uniform(2.0, 40.0, (N, H, W)).astype(np.float32)
+    T = np.tile(np.eye(4, dtype=np.float32), (N, 1, 1))
+    w = rng.standard_normal((N, 3)) * 0.02
+    for n in range(N):
+        wx, wy, wz = w[n]
+        T[n, :3, :3] += np.array([[0, -wz, wy], [wz, 0, -wx], [-wy, wx, 0]], np.float32)
+    T[:, :3, 3] = rng.standard_normal((N, 3)).astype(np.float32) * np.array([0.54, 0.05, 0.3], np.float32)
+    K = np.stack([np.full(N, 0.58 * W), np.full(N, 1.92 * H), np.full(N, 0.49 * W), np.full(N, 0.5 * H)], 1).astype(np.float32)
+    K += rng.standard_normal(K.shape).astype(np.float32)
+    img = rng.uniform(0, 1, (N, C, H, W)).astype(np.float32)
+    tgt = rng.uniform(0, 1, (N, C, H, W)).astype(np.float32)
+    return depth, T, K, img, tgt
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 52, 3), (3, 37, 61, 1), (4, 128, 416, 3), (1, 20, 33, 8)])
+def test_caffe_layers_vs_oracle(ops, oracle, shape):
+    import geo_transform as gt
+    N, H, W, C = shape
+    depth, T, K, img, tgt = _caffe_case(N, H, W, C, seed=sum(shape))
+    d = cu(depth[:, None]).requires_grad_(True)
+    Tt = cu(T[:, None]).requires_grad_(True)
+    Kt = cu(K[:, :, None, None]).requires_grad_(True)
+    im = cu(img).requires_grad_(True)
+    pts = gt.geo_transform(d, Tt, Kt)
+    xy = gt.pin_hole_project(pts, Kt)
+    wr = gt.inverse_warp(im, xy)
+    loss = gt.abs_loss(wr, cu(tgt))
+    # forward: same expressions, same roundings -> bit-exact
+    o_pts = oracle.caffe_geo_fwd(depth, T, K)
+    o_xy = oracle.caffe_pinhole_fwd(o_pts, K)
+    o_wr = oracle.caffe_warp_fwd(img, o_xy)
+    o_loss, o_ga, _ = oracle.caffe_abs_loss(o_wr, tgt)
+    assert np.array_equal(npy(pts), o_pts)
+    assert np.array_equal(npy(xy), o_xy)
+    assert np.array_equal(npy(wr), o_wr)
+    assert abs(float(loss) - o_loss) <= 1e-6 * abs(o_loss)
+    loss.backward()
+    o_gi, o_gxy = oracle.caffe_warp_bwd(o_ga, img, o_xy)
+    o_gp, o_gK2 = oracle.caffe_pinhole_bwd(o_gxy, o_pts, K)
+    o_gd, o_gT, o_gK1 = oracle.caffe_geo_bwd(o_gp, depth, T, K)
+    assert_close(npy(im.grad), o_gi, what="img_diff")                 # atomics: order differs
+    assert np.array_equal(npy(d.grad)[:, 0], o_gd)                    # per-pixel chain: bit-exact
+    assert_close(npy(Tt.grad).reshape(N, 16), o_gT, tol=2e-5, what="T_diff")   # fp32 tree sum vs fp64 ordered sum
+    assert_close(npy(Kt.grad).reshape(N, 4), o_gK1 + o_gK2, tol=2e-5, what="K_diff")
+    assert np.all(npy(Tt.grad).reshape(N, 16)[:, 12:] == 0)
+
+
+def test_caffe_layers_edge_cases(ops, oracle):
+    import geo_transform as gt
+    N, H, W, C = 2, 12, 20, 3
+    depth, T, K, img, tgt = _caffe_case(N, H, W, C, seed=5)
+    # coordinates far outside, exactly on the border, negative, and a zero-depth pixel (Z + 1e-12 path)
+    xy = np.zeros((N, 2, H, W), np.float32)
+    rng = np.random.default_rng(1)
+    xy[:, 0] = rng.uniform(-3, W + 2, (N, H, W))
+    xy[:, 1] = rng.uniform(-3, H + 2, (N, H, W))
+    xy[0, :, 0, 0] = (W - 1, H - 1)
+    xy[0, :, 0, 1] = (-1.0, -1.0)
+    xy[0, :, 0, 2] = (1e9, -1e9)
+    xy[0, :, 0, 3] = (0.0, 0.0)
+    out = gt.inverse_warp(cu(img), cu(xy))
+    assert np.array_equal(npy(out), oracle.caffe_warp_fwd(img, xy))
+    g = rng.standard_normal(img.shape).astype(np.float32)
+    x = cu(xy).requires_grad_(True)
+    gt.inverse_warp(cu(img), x).backward(cu(g))
+    assert np.array_equal(npy(x.grad), oracle.caffe_warp_bwd(g, img, xy, need_gimg=False)[1])
+    depth[0, 0, 0] = 0.0
+    pts = oracle.caffe_geo_fwd(depth, T, K)
+    pts[1, 2, 3, 3] = 0.0
+    got = gt.pin_hole_project(cu(pts), cu(K[:, :, None, None]))
+    assert np.array_equal(npy(got), oracle.caffe_pinhole_fwd(pts, K), equal_nan=True)
+    # sign(0) = -1 in AbsLoss
+    a = cu(img).requires_grad_(True)
+    gt.abs_loss(a, cu(img)).backward()
+    assert np.all(npy(a.grad) == np.float32(-1.0 / N))
+    with pytest.raises(Exception):
+        gt.geo_transform(torch.zeros(1, 1, 4, 4), torch.eye(4).view(1, 1, 4, 4), torch.ones(1, 4, 1, 1))   # CPU tensors
+    with pytest.raises(AssertionError):
+        gt.pin_hole_project(cu(pts[:, :2]), cu(K[:, :, None, None]))
+
+
+def test_caffe_chain_matches_pytorch_convention(ops, oracle):
+    """The Caffe-era and PyTorch-era formulations describe the same warp: with K = (fx,fy,cx,cy) and the same
+    rigid motion, pixel-space sampling (Caffe) equals grid_sample(align_corners=False) up to the reference's known
+    (W-1) normalisation shift -- so compare against the closed form instead: identity motion returns the image."""
+    import geo_transform as gt
+    N, H, W, C = 2, 24, 40, 3
+    depth, T, K, img, _ = _caffe_case(N, H, W, C, seed=9)
+    T[:] = np.eye(4, dtype=np.float32)
+    xy = gt.pin_hole_project(gt.geo_transform(cu(depth[:, None]), cu(T[:, None]), cu(K[:, :, None, None])), cu(K[:, :, None, None]))
+    xs, ys = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
+    assert np.abs(npy(xy)[:, 0] - xs).max() < 1e-3 and np.abs(npy(xy)[:, 1] - ys).max() < 1e-3
+    out = gt.inverse_warp(cu(img), cu(np.broadcast_to(np.stack([xs, ys])[None], (N, 2, H, W)).copy()))
+    assert np.array_equal(npy(out), img)
