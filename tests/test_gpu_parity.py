@@ -602,7 +602,7 @@ def test_caffe_layers_vs_oracle(ops, oracle, shape):
     assert np.array_equal(npy(pts), o_pts)
     assert np.array_equal(npy(xy), o_xy)
     assert np.array_equal(npy(wr), o_wr)
-    assert abs(float(loss) - o_loss) <= 1e-6 * abs(o_loss)
+    assert abs(float(loss.detach()) - o_loss) <= 1e-6 * abs(o_loss)
     loss.backward()
     o_gi, o_gxy = oracle.caffe_warp_bwd(o_ga, img, o_xy)
     o_gp, o_gK2 = oracle.caffe_pinhole_bwd(o_gxy, o_pts, K)
