@@ -8,6 +8,7 @@
 // bilinear taps per channel are read-only gathers served by L1/L2.
 #include "dvf_internal.h"
 #include "dvf_math.cuh"
+#include "dvf_math2.cuh"
 #include "dvf_reduce.cuh"
 
 namespace dvf {
@@ -18,6 +19,7 @@ struct WarpParams {
   Geo geo;
   int allow_fast, zeros_padding;
   int blocks_per_image;
+  int bwd_blocks_per_image, bwd_iters;   // backward: a CTA walks bwd_iters chunks of 2*kThreads pixels (amortises its reduction)
   const float* img;
   const float* depth;
   const float* P;
@@ -96,8 +98,8 @@ template <bool kZeros>
 __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_kernel(const __grid_constant__ WarpParams p) {
   __shared__ float s_red[kThreads / 32][kRedSlots];
   __shared__ int s_flag;
-  const int b = blockIdx.x / p.blocks_per_image;
-  const int chunk = blockIdx.x - b * p.blocks_per_image;
+  const int b = blockIdx.x / p.bwd_blocks_per_image;
+  const int chunk0 = (blockIdx.x - b * p.bwd_blocks_per_image) * p.bwd_iters;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float P[12], M[9];
   load_PM(p, b, P, M);
@@ -109,10 +111,9 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_kernel(const __grid
 #pragma unroll
   for (int k = 0; k < kRedSlots; ++k) acc[k] = 0.0f;
 
-#pragma unroll
-  for (int q = 0; q < kWarpPPT; ++q) {
-    const int idx = chunk * (kThreads * kWarpPPT) + q * kThreads + tid;
-    if (idx >= HW) continue;
+  for (int it = 0; it < p.bwd_iters * kWarpPPT; ++it) {
+    const int idx = chunk0 * (kThreads * kWarpPPT) + it * kThreads + tid;
+    if (idx >= HW) break;
     const int i = (int)fastdiv((uint32_t)idx, p.divW), j = idx - i * W;
     Cam cam;
     Proj pr;
@@ -161,14 +162,226 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_kernel(const __grid
   }
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_flag = (atomicAdd(p.img_counter + b, 1u) == (unsigned)(p.blocks_per_image - 1));
+  if (tid == 0) s_flag = (atomicAdd(p.img_counter + b, 1u) == (unsigned)(p.bwd_blocks_per_image - 1));
   __syncthreads();
   if (!s_flag) return;
   __threadfence();
-  const float* img_part = p.partials + (size_t)b * p.blocks_per_image * kRedSlots;
+  const float* img_part = p.partials + (size_t)b * p.bwd_blocks_per_image * kRedSlots;
   if (tid < 12 * 8) {
     const int s = tid >> 3;
-    const double sum = group8_sum(img_part + s, p.blocks_per_image, kRedSlots, tid & 7);
+    const double sum = group8_sum(img_part + s, p.bwd_blocks_per_image, kRedSlots, tid & 7);
+    if ((tid & 7) == 0) p.gP[(size_t)b * 12 + s] = (float)sum;
+  }
+  if (tid == 0) p.img_counter[b] = 0u;
+}
+
+// ---- C == 3, packed: a thread owns two adjacent pixels and runs the coordinate chain on (A,B) pairs with FFMA2 /
+// FMUL2 / FADD2 (dvf_math2.cuh; every half rounded like the scalar op => same bits as the kernels above), 8-byte
+// streaming loads / stores.  Needs HW even and 8-byte aligned depth / output planes (checked on the host).
+struct PairCtx {
+  Cam2 cam;
+  Proj2 pr;
+  Loc2 L;
+  bool fastA, fastB;
+};
+
+template <bool kZeros>
+__device__ __forceinline__ void pair_forward(const WarpParams& p, const float (&P)[12], const float (&M)[9], const Geo2& geo2,
+                                             float depth_max, int b, int idxA, f2 dep, PairCtx& x) {
+  const int W = p.W;
+  const int iA = (int)fastdiv((uint32_t)idxA, p.divW), jA = idxA - iA * W;
+  const int iB = (int)fastdiv((uint32_t)(idxA + 1), p.divW), jB = idxA + 1 - iB * W;
+  pixel_to_cam2(M, dep, make_float2((float)iA, (float)iB), make_float2((float)jA, (float)jB), x.cam);
+  x.fastA = fabsf(dep.x) <= depth_max;   // false for NaN
+  x.fastB = fabsf(dep.y) <= depth_max;
+  project2<kZeros>(P, x.cam, geo2, x.pr);
+  if (__builtin_expect(!(x.fastA && x.fastB), 0)) {   // redo the offending lane(s) with exact divisions
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 0 ? x.fastA : x.fastB) continue;
+      Cam c1;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        c1.ray[q] = h == 0 ? x.cam.ray[q].x : x.cam.ray[q].y;
+        c1.cam[q] = h == 0 ? x.cam.cam[q].x : x.cam.cam[q].y;
+      }
+      const Proj e = warp_project_exact<kZeros>(p.P + b * 12, c1, p.geo);
+      Proj2& pr = x.pr;
+      if (h == 0) {
+        pr.qz.x = e.qz; pr.nZ.x = -e.Z; pr.u.x = e.u; pr.v.x = e.v; pr.xn.x = e.xn; pr.yn.x = e.yn; pr.mxA = e.mx; pr.myA = e.my;
+      } else {
+        pr.qz.y = e.qz; pr.nZ.y = -e.Z; pr.u.y = e.u; pr.v.y = e.v; pr.xn.y = e.xn; pr.yn.y = e.yn; pr.mxB = e.mx; pr.myB = e.my;
+      }
+    }
+  }
+  locate2<kZeros>(x.pr.xn, x.pr.yn, p.H, W, p.geo, geo2, x.L);
+}
+
+// the four taps of one channel plane for both pixels; pa / pb point at the north-west texel of A / B
+__device__ __forceinline__ void pair_taps(const Loc2& L, const float* pa, const float* pb, int W, f2& t00, f2& t01, f2& t10, f2& t11) {
+  const float* pa1 = ptr_off(pa, W);
+  const float* pb1 = ptr_off(pb, W);
+  t00 = make_float2(L.nwA ? __ldg(pa) : 0.0f, L.nwB ? __ldg(pb) : 0.0f);
+  t01 = make_float2(L.neA ? __ldg(pa + 1) : 0.0f, L.neB ? __ldg(pb + 1) : 0.0f);
+  t10 = make_float2(L.swA ? __ldg(pa1) : 0.0f, L.swB ? __ldg(pb1) : 0.0f);
+  t11 = make_float2(L.seA ? __ldg(pa1 + 1) : 0.0f, L.seB ? __ldg(pb1 + 1) : 0.0f);
+}
+
+__device__ __forceinline__ float pair_depth_max(const WarpParams& p, const float (&P)[12], const float (&M)[9]) {
+  bool ok = p.allow_fast != 0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) ok = ok && (fabsf(M[k]) <= 1048576.0f);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) ok = ok && (fabsf(P[k]) <= 1073741824.0f);
+  return ok ? 1073741824.0f : -1.0f;   // same guard as the fused loss kernel (dvf_loss_kernel.cuh)
+}
+
+__device__ __forceinline__ f2 ld_stream2(const float* p) {
+  f2 v;
+  asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream2(float* p, f2 v) {
+  asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+template <bool kZeros>
+__global__ void __launch_bounds__(kThreads) inverse_warp_fwd_c3x2_kernel(const __grid_constant__ WarpParams p) {
+  const int b = blockIdx.x / p.blocks_per_image;
+  const int chunk = blockIdx.x - b * p.blocks_per_image;
+  const int HW = p.HW, W = p.W;
+  const int idxA = chunk * (kThreads * 2) + 2 * threadIdx.x;
+  if (idxA >= HW) return;   // HW is even: a pair is never split by the end of the image
+  float P[12], M[9];
+  load_PM(p, b, P, M);
+  const Geo2 geo2 = make_geo2(p.geo);
+  const float depth_max = pair_depth_max(p, P, M);
+  const float* img_b = p.img + (size_t)b * 3 * HW;
+  float* out_b = p.warped + (size_t)b * 3 * HW;
+  PairCtx x;
+  pair_forward<kZeros>(p, P, M, geo2, depth_max, b, idxA, ld_stream2(p.depth + (size_t)b * HW + idxA), x);
+  const Loc2& L = x.L;
+  const f2 wnw = mul2(L.s, L.e), wne = mul2(L.s, L.w), wsw = mul2(L.n, L.e), wse = mul2(L.n, L.w);
+  const float* pa = ptr_off(img_b, L.y0A * W + L.x0A);
+  const float* pb = ptr_off(img_b, L.y0B * W + L.x0B);
+  bool anyA = false, anyB = false;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    f2 t00, t01, t10, t11;
+    pair_taps(L, pa, pb, W, t00, t01, t10, t11);
+    const f2 wv = bilerp2(t00, t01, t10, t11, wnw, wne, wsw, wse);
+    anyA |= (wv.x != 0.0f);
+    anyB |= (wv.y != 0.0f);
+    st_stream2(out_b + (size_t)c * HW + idxA, wv);
+    pa = ptr_off(pa, HW);
+    pb = ptr_off(pb, HW);
+  }
+  if (p.valid) *reinterpret_cast<uchar2*>(p.valid + (size_t)b * HW + idxA) = make_uchar2(anyA ? 1 : 0, anyB ? 1 : 0);
+}
+
+template <bool kZeros>
+__global__ void __launch_bounds__(kThreads) inverse_warp_bwd_c3x2_kernel(const __grid_constant__ WarpParams p) {
+  __shared__ float s_red[kThreads / 32][kRedSlots];
+  __shared__ int s_flag;
+  const int b = blockIdx.x / p.bwd_blocks_per_image;
+  const int chunk0 = (blockIdx.x - b * p.bwd_blocks_per_image) * p.bwd_iters;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int HW = p.HW, W = p.W;
+  float acc[kRedSlots];
+#pragma unroll
+  for (int k = 0; k < kRedSlots; ++k) acc[k] = 0.0f;
+  float P[12], M[9];
+  load_PM(p, b, P, M);
+  const Geo2 geo2 = make_geo2(p.geo);
+  const float depth_max = pair_depth_max(p, P, M);
+  const float* img_b = p.img + (size_t)b * 3 * HW;
+#pragma unroll 1
+  for (int it = 0; it < p.bwd_iters; ++it) {
+    const int idxA = (chunk0 + it) * (kThreads * 2) + 2 * tid;
+    if (idxA >= HW) break;
+    const float* gout_b = p.gout + (size_t)b * 3 * HW + idxA;
+    PairCtx x;
+    pair_forward<kZeros>(p, P, M, geo2, depth_max, b, idxA, ld_stream2(p.depth + (size_t)b * HW + idxA), x);
+    const Loc2& L = x.L;
+    const float* pa = ptr_off(img_b, L.y0A * W + L.x0A);
+    const float* pb = ptr_off(img_b, L.y0B * W + L.x0B);
+    f2 gx = dup(0.0f), gy = dup(0.0f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      f2 t00, t01, t10, t11;
+      pair_taps(L, pa, pb, W, t00, t01, t10, t11);
+      bilerp_grad2(t00, t01, t10, t11, L, ld_stream2(gout_b + (size_t)c * HW), gx, gy);
+      pa = ptr_off(pa, HW);
+      pb = ptr_off(pb, HW);
+    }
+    ChainGrad2 cg;
+    chain_backward2(P, x.cam, x.pr, L, gx, gy, geo2, cg);
+    if (__builtin_expect(!(x.fastA && x.fastB), 0)) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h == 0 ? x.fastA : x.fastB) continue;
+        Cam c1;
+        Proj p1;
+        Loc L1;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          c1.ray[q] = h == 0 ? x.cam.ray[q].x : x.cam.ray[q].y;
+          c1.cam[q] = h == 0 ? x.cam.cam[q].x : x.cam.cam[q].y;
+        }
+        const Proj2& pr = x.pr;
+        p1.qz = h == 0 ? pr.qz.x : pr.qz.y;
+        p1.Z = h == 0 ? -pr.nZ.x : -pr.nZ.y;
+        p1.rZ = 0.0f;
+        p1.u = h == 0 ? pr.u.x : pr.u.y;
+        p1.v = h == 0 ? pr.v.x : pr.v.y;
+        p1.xn = h == 0 ? pr.xn.x : pr.xn.y;
+        p1.yn = h == 0 ? pr.yn.x : pr.yn.y;
+        p1.mx = h == 0 ? pr.mxA : pr.mxB;
+        p1.my = h == 0 ? pr.myA : pr.myB;
+        L1.x0 = L1.y0 = 0;
+        L1.w = L1.e = L1.n = L1.s = 0.0f;
+        L1.bnw = L1.bne = L1.bsw = L1.bse = false;
+        L1.gmx = h == 0 ? L.gmx.x : L.gmx.y;
+        L1.gmy = h == 0 ? L.gmy.x : L.gmy.y;
+        const ChainGrad e = warp_chain_backward_exact(p.P + b * 12, c1, p1, L1, h == 0 ? gx.x : gx.y, h == 0 ? gy.x : gy.y, p.geo);
+        if (h == 0) {
+          cg.gq[0].x = e.gq[0]; cg.gq[1].x = e.gq[1]; cg.gq[2].x = e.gq[2]; cg.gdepth.x = e.gdepth;
+        } else {
+          cg.gq[0].y = e.gq[0]; cg.gq[1].y = e.gq[1]; cg.gq[2].y = e.gq[2]; cg.gdepth.y = e.gdepth;
+        }
+      }
+    }
+    st_stream2(p.gdepth + (size_t)b * HW + idxA, cg.gdepth);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const f2 t = mul2(cg.gq[r], x.cam.cam[k]);   // the scalar kernel accumulates with fmaf per pixel; the order
+        acc[r * 4 + k] += t.x + t.y;                 // of a sum over pixels is free (dP is compared at 1e-5)
+      }
+      acc[r * 4 + 3] += cg.gq[r].x + cg.gq[r].y;
+    }
+  }
+
+  const float r = butterfly16(acc, lane);
+  if ((lane & 1) == 0) s_red[warp][butterfly_slot(lane)] = r;
+  __syncthreads();
+  if (tid < kRedSlots) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w8 = 0; w8 < kThreads / 32; ++w8) t += s_red[w8][tid];
+    __stcg(p.partials + (size_t)blockIdx.x * kRedSlots + tid, t);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_flag = (atomicAdd(p.img_counter + b, 1u) == (unsigned)(p.bwd_blocks_per_image - 1));
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  const float* img_part = p.partials + (size_t)b * p.bwd_blocks_per_image * kRedSlots;
+  if (tid < 12 * 8) {
+    const int s = tid >> 3;
+    const double sum = group8_sum(img_part + s, p.bwd_blocks_per_image, kRedSlots, tid & 7);
     if ((tid & 7) == 0) p.gP[(size_t)b * 12 + s] = (float)sum;
   }
   if (tid == 0) p.img_counter[b] = 0u;
@@ -234,6 +447,13 @@ static int fill_params(const dvf_desc* d, WarpParams& p) {
   p.allow_fast = d->W > 1 && d->H > 1;
   p.zeros_padding = d->padding == DVF_PAD_ZEROS;
   p.blocks_per_image = (p.HW + kThreads * kWarpPPT - 1) / (kThreads * kWarpPPT);
+  // backward: about 8 CTAs per SM over the whole batch, each walking several chunks, so that the CTA reduction and
+  // its ticket are paid once per few thousand pixels
+  int want = (num_sms() * 8 + p.B - 1) / p.B;
+  if (want < 1) want = 1;
+  if (want > p.blocks_per_image) want = p.blocks_per_image;
+  p.bwd_iters = (p.blocks_per_image + want - 1) / want;
+  p.bwd_blocks_per_image = (p.blocks_per_image + p.bwd_iters - 1) / p.bwd_iters;
   return DVF_OK;
 }
 
@@ -254,10 +474,17 @@ DVF_EXPORT int dvf_inverse_warp_fwd(const dvf_desc* d, const void* img, const fl
   p.Kinv = Kinv;
   p.warped = static_cast<float*>(warped);
   p.valid = valid;
-  if (p.zeros_padding)
-    inverse_warp_fwd_kernel<true><<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  else
-    inverse_warp_fwd_kernel<false><<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)(p.blocks_per_image * p.B);
+  // images: packed pixel pairs (needs an even HW and 8-byte aligned planes); anything else: generic kernel
+  const bool packed = p.C == 3 && p.HW % 2 == 0 && aligned(depth, 8) && aligned(warped, 8) && (!valid || aligned(valid, 2));
+  if (packed) {
+    if (p.zeros_padding) inverse_warp_fwd_c3x2_kernel<true><<<grid, kThreads, 0, cs>>>(p);
+    else inverse_warp_fwd_c3x2_kernel<false><<<grid, kThreads, 0, cs>>>(p);
+  } else {
+    if (p.zeros_padding) inverse_warp_fwd_kernel<true><<<grid, kThreads, 0, cs>>>(p);
+    else inverse_warp_fwd_kernel<false><<<grid, kThreads, 0, cs>>>(p);
+  }
   return launch_status();
 }
 
@@ -289,10 +516,16 @@ DVF_EXPORT int dvf_inverse_warp_bwd(const dvf_desc* d, const void* gout, const v
   p.partials = static_cast<float*>(workspace);
   p.img_counter = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) +
                                               align_up((size_t)p.blocks_per_image * p.B * kRedSlots * sizeof(float), 256));
-  if (p.zeros_padding)
-    inverse_warp_bwd_kernel<true><<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  else
-    inverse_warp_bwd_kernel<false><<<p.blocks_per_image * p.B, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)(p.bwd_blocks_per_image * p.B);
+  const bool packed = p.C == 3 && !p.gimg && p.HW % 2 == 0 && aligned(depth, 8) && aligned(gdepth, 8) && aligned(gout, 8);
+  if (packed) {
+    if (p.zeros_padding) inverse_warp_bwd_c3x2_kernel<true><<<grid, kThreads, 0, cs>>>(p);
+    else inverse_warp_bwd_c3x2_kernel<false><<<grid, kThreads, 0, cs>>>(p);
+  } else {
+    if (p.zeros_padding) inverse_warp_bwd_kernel<true><<<grid, kThreads, 0, cs>>>(p);
+    else inverse_warp_bwd_kernel<false><<<grid, kThreads, 0, cs>>>(p);
+  }
   return launch_status();
 }
 

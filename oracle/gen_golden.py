@@ -148,6 +148,34 @@ def case_se3(name, B, seed):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), kind="se3", vec=_np(vec), out=_np(out), gout=_np(gout), gvec=_np(x.grad))
 
 
+def case_regularisers(mods, name, B, H, W, n_scales, seed):
+    """smooth_loss (loss_functions.py:23-41, scale_factor 2) and explainability_loss (loss_functions_sfm.py:49-56)
+    of the reference, value and autograd gradients; the masks include the ends of [0, 1] and denormals."""
+    rng = np.random.default_rng(seed)
+    maps = [syn.depth(B, H >> s, W >> s, seed + s).unsqueeze(1) for s in range(n_scales)]
+    maps[0][:, :, ::2] = torch.round(maps[0][:, :, ::2])       # exact zeros among the second differences
+    maps.append(torch.from_numpy(rng.uniform(1, 9, (1, 1, 3, 5)).astype(np.float32)))     # smaller than a strip
+    t = [m.clone().requires_grad_(True) for m in maps]
+    val = mods["loss_functions"].smooth_loss(t, 2.0)
+    val.backward()
+    out = dict(kind="regularisers", n_maps=len(maps), smooth=_np(val))
+    for i, (m, x) in enumerate(zip(maps, t)):
+        out[f"map{i}"] = _np(m)
+        out[f"g_map{i}"] = _np(x.grad)
+    masks = [syn.explainability(B, 2, H >> s, W >> s, seed + 10 + s) for s in range(n_scales - 1)]
+    edge = np.array([0.0, 1.0, 1e-30, 1e-12, 0.5, 1.0 - 2.0 ** -24, 1e-45, 0.999, 2.0 ** -126, 0.25], np.float32)
+    masks.append(torch.from_numpy(np.tile(edge, 6).reshape(1, 2, 5, 6).copy()))
+    tm = [m.clone().requires_grad_(True) for m in masks]
+    ev = mods["loss_functions_sfm"].explainability_loss(tm)
+    ev.backward()
+    out["n_masks"] = len(masks)
+    out["expl"] = _np(ev)
+    for i, (m, x) in enumerate(zip(masks, tm)):
+        out[f"mask{i}"] = _np(m)
+        out[f"g_mask{i}"] = _np(x.grad)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
 def main():
     warnings.filterwarnings("ignore")
     torch.set_num_threads(1)
@@ -165,6 +193,7 @@ def main():
     case_sfm(mods, "sfm_2scales_nomask_quat_border", 2, 32, 104, 2, seed=10, with_mask=False, rot="quat", pad="border")
     case_sfm(mods, "sfm_old_2scales_mask", 2, 32, 104, 2, seed=11, with_mask=True, rot="euler", pad="zeros", old=True)
     case_se3("se3_exp", 6, seed=12)
+    case_regularisers(mods, "regularisers", 2, 30, 52, 3, seed=13)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("wrote", sorted(os.listdir(OUT)), f"{tot / 1024:.0f} KiB")
 

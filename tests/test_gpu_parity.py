@@ -661,3 +661,59 @@ def test_caffe_chain_matches_pytorch_convention(ops, oracle):
     assert np.abs(npy(xy)[:, 0] - xs).max() < 1e-3 and np.abs(npy(xy)[:, 1] - ys).max() < 1e-3
     out = gt.inverse_warp(cu(img), cu(np.broadcast_to(np.stack([xs, ys])[None], (N, 2, H, W)).copy()))
     assert np.array_equal(npy(out), img)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 5), (2, 2, 2), (3, 7, 9), (2, 6, 3), (1, 5, 1), (2, 3, 300), (1, 130, 2), (2, 9, 33)])
+def test_smooth_loss_small_and_ragged_maps(ops, oracle, shape):
+    """strips of 4 rows per thread: heights that are not multiples of 4, maps narrower / shorter than a stencil
+    (terms whose element count is 0 contribute NaN in the reference -- mean of an empty tensor -- so only shapes
+    with H, W >= 3 are compared in value; smaller ones must simply not crash or touch memory out of bounds)"""
+    B, H, W = shape
+    rng = np.random.default_rng(H * 100 + W)
+    m = rng.uniform(1.0, 30.0, (B, H, W)).astype(np.float32)
+    m[:, :: 2] = np.round(m[:, :: 2])          # exact zeros among the second differences: sign(0) = 0
+    t = cu(m[:, None]).requires_grad_(True)
+    val = ops.smooth_loss([t])
+    val.backward()
+    torch.cuda.synchronize()
+    if H >= 3 and W >= 3:
+        v, g = oracle.smooth_loss_one(m, need_grad=True)
+        assert abs(val.item() - v) <= RTOL_F32 * max(abs(v), 1e-30)
+        assert_close(npy(t.grad[:, 0]), g, what="smooth grad")
+    else:
+        assert t.grad.shape == t.shape
+
+
+def test_explainability_loss_edge_values(ops, oracle):
+    """mask values at and beyond the ends of (0, 1): log clamp at -100, gradient denominator clamp at 1e-12, NaN"""
+    # (the reference's binary_cross_entropy rejects values outside [0, 1]; NaN is let through)
+    m = np.array([0.0, 1.0, 1e-30, 1e-12, 0.5, 1.0 - 2.0 ** -24, 1e-45, 0.999, np.nan, 2.0 ** -126, 0.25, 1e-7], np.float32)
+    m = np.tile(m, 11)[: 125].reshape(1, 1, 5, 25).copy()
+    t = cu(m).requires_grad_(True)
+    val = ops.explainability_loss([t])
+    val.backward()
+    v, g = oracle.explainability_loss_one(m, need_grad=True)
+    fin = np.isfinite(g)
+    assert np.array_equal(np.isfinite(npy(t.grad)), fin)
+    assert_close(npy(t.grad)[fin], g[fin], what="expl grad")
+    assert np.array_equal(npy(t.grad)[~fin], g[~fin], equal_nan=True)
+    assert (np.isnan(v) and np.isnan(val.item())) or abs(val.item() - v) <= RTOL_F32 * abs(v)
+
+
+def test_regularisers_dropins_vs_reference_golden(ops):
+    """the drop-in smooth_loss / explainability_loss against the reference's own values and gradients"""
+    import loss_functions as lf
+    import loss_functions_sfm as sfm
+    g = golden("regularisers")
+    t = [cu(g[f"map{i}"]).requires_grad_(True) for i in range(int(g["n_maps"]))]
+    val = lf.smooth_loss(t, 2.0)
+    val.backward()
+    assert abs(val.item() - float(g["smooth"])) <= RTOL_F32 * float(g["smooth"])
+    for i, x in enumerate(t):
+        assert_close(npy(x.grad), g[f"g_map{i}"], what=f"smooth grad {i}")
+    tm = [cu(g[f"mask{i}"]).requires_grad_(True) for i in range(int(g["n_masks"]))]
+    ev = sfm.explainability_loss(tm)
+    ev.backward()
+    assert abs(ev.item() - float(g["expl"])) <= RTOL_F32 * float(g["expl"])
+    for i, x in enumerate(tm):
+        assert_close(npy(x.grad), g[f"g_mask{i}"], what=f"expl grad {i}")

@@ -100,3 +100,24 @@ def test_se3_exp_golden(oracle):
     assert np.abs(out - g["out"][:, 0]).max() < 1e-12
     gin = oracle.se3_exp_bwd(g["vec"], g["gout"])
     assert_close(gin, g["gvec"].reshape(-1, 6), tol=1e-6, what="se3 grad")
+
+
+def test_regularisers_match_reference_golden(oracle):
+    """oracle smooth / explainability terms against the reference's own values and autograd gradients
+    (tests/golden/regularisers.npz, generated by oracle/gen_golden.py from loss_functions.py:23-41 and
+    loss_functions_sfm.py:49-56)"""
+    from helpers import assert_close, golden
+    g = golden("regularisers")
+    ref, w = 0.0, 1.0
+    for i in range(int(g["n_maps"])):
+        v, gr = oracle.smooth_loss_one(g[f"map{i}"][:, 0], need_grad=True)
+        ref += v * w
+        assert_close(w * gr, g[f"g_map{i}"][:, 0], what=f"smooth grad {i}")
+        w /= 2.0
+    assert abs(ref - float(g["smooth"])) <= 1e-5 * float(g["smooth"])
+    ref = 0.0
+    for i in range(int(g["n_masks"])):
+        v, gr = oracle.explainability_loss_one(g[f"mask{i}"], need_grad=True)
+        ref += v
+        assert_close(gr, g[f"g_mask{i}"], what=f"expl grad {i}")
+    assert abs(ref - float(g["expl"])) <= 1e-5 * float(g["expl"])
