@@ -9,6 +9,7 @@
 // CTA (shared memory) and one atomic per CTA and entry reaches memory.
 #include "dvf_internal.h"
 #include "dvf_math.cuh"
+#include "dvf_reduce.cuh"
 
 namespace dvf {
 
@@ -53,45 +54,48 @@ __global__ void __launch_bounds__(kThreads) caffe_geo_fwd_kernel(const float* __
     pts[((size_t)n * 3 + r) * HW + idx] = add(add(add(mul(t[r * 4], X), mul(t[r * 4 + 1], Y)), mul(t[r * 4 + 2], d)), t[r * 4 + 3]);
 }
 
+constexpr int kGeoBwdPx = 8;   // pixels per thread of the GeoTransform backward: its 16 sums are folded once per CTA
+
 __global__ void __launch_bounds__(kThreads) caffe_geo_bwd_kernel(const float* __restrict__ top, const float* __restrict__ depth,
                                                                 const float* __restrict__ T, const float* __restrict__ K, int H,
                                                                 int W, float* __restrict__ depth_diff, float* __restrict__ T_diff,
                                                                 float* __restrict__ K_diff) {
-  const int n = blockIdx.y, HW = H * W, idx = blockIdx.x * kThreads + threadIdx.x;
+  const int n = blockIdx.y, HW = H * W;
   const float* t = T + n * 16;
   const float fx = K[n * 4], fy = K[n * 4 + 1], cx = K[n * 4 + 2], cy = K[n * 4 + 3];
-  float acc[16];
+  float acc[kRedSlots];   // 0..11: dT rows 0-2, 12..15: d(fx, fy, cx, cy)
 #pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.0f;
-  if (idx < HW) {
+  for (int k = 0; k < kRedSlots; ++k) acc[k] = 0.0f;
+#pragma unroll 2
+  for (int j = 0; j < kGeoBwdPx; ++j) {
+    const int idx = (blockIdx.x * kGeoBwdPx + j) * kThreads + threadIdx.x;
+    if (idx >= HW) break;
     const int y = idx / W, x = idx - y * W;
-    const float g[3] = {top[((size_t)n * 3 + 0) * HW + idx], top[((size_t)n * 3 + 1) * HW + idx], top[((size_t)n * 3 + 2) * HW + idx]};
-    const float bX = div(sub((float)x, cx), fx), bY = div(sub((float)y, cy), fy), d = depth[(size_t)n * HW + idx];
+    const float g[3] = {ld_stream(top + ((size_t)n * 3 + 0) * HW + idx), ld_stream(top + ((size_t)n * 3 + 1) * HW + idx),
+                        ld_stream(top + ((size_t)n * 3 + 2) * HW + idx)};
+    const float bX = div(sub((float)x, cx), fx), bY = div(sub((float)y, cy), fy), d = ld_stream(depth + (size_t)n * HW + idx);
     float dd = 0.0f;
 #pragma unroll
     for (int r = 0; r < 3; ++r) dd = add(dd, mul(g[r], add(add(mul(t[r * 4], bX), mul(t[r * 4 + 1], bY)), t[r * 4 + 2])));
-    if (depth_diff) depth_diff[(size_t)n * HW + idx] = dd;
+    if (depth_diff) st_stream(depth_diff + (size_t)n * HW + idx, dd);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      acc[r * 4 + 0] = mul(mul(g[r], bX), d);
-      acc[r * 4 + 1] = mul(mul(g[r], bY), d);
-      acc[r * 4 + 2] = mul(g[r], d);
-      acc[r * 4 + 3] = g[r];
+      acc[r * 4 + 0] += mul(mul(g[r], bX), d);
+      acc[r * 4 + 1] += mul(mul(g[r], bY), d);
+      acc[r * 4 + 2] += mul(g[r], d);
+      acc[r * 4 + 3] += g[r];
     }
     const float sx = add(add(mul(g[0], t[0]), mul(g[1], t[4])), mul(g[2], t[8]));
     const float sy = add(add(mul(g[0], t[1]), mul(g[1], t[5])), mul(g[2], t[9]));
-    acc[12] = mul(sx, mul(div(-bX, fx), d));    // d/dfx
-    acc[13] = mul(sy, mul(div(-bY, fy), d));    // d/dfy
-    acc[14] = mul(sx, div(-d, fx));             // d/dcx
-    acc[15] = mul(sy, div(-d, fy));             // d/dcy
+    acc[12] += mul(sx, mul(div(-bX, fx), d));    // d/dfx
+    acc[13] += mul(sy, mul(div(-bY, fy), d));    // d/dfy
+    acc[14] += mul(sx, div(-d, fx));             // d/dcx
+    acc[15] += mul(sy, div(-d, fy));             // d/dcy
   }
-  __shared__ float s[kThreads / 32][16];
+  __shared__ float s[kThreads / 32][kRedSlots];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const float r = warp_sum(acc[k]);
-    if (lane == 0) s[warp][k] = r;
-  }
+  const float r = butterfly16(acc, lane);          // 15 shuffles fold all 16 sums over the warp
+  if ((lane & 1) == 0) s[warp][butterfly_slot(lane)] = r;
   __syncthreads();
   if (threadIdx.x < 16) {
     float v = 0.0f;
@@ -137,48 +141,77 @@ __global__ void __launch_bounds__(kThreads) caffe_pinhole_bwd_kernel(const float
   if (K_diff) cta_atomic_add<4>(acc, K_diff + n * 4);
 }
 
-__global__ void __launch_bounds__(kThreads) caffe_warp_fwd_kernel(const float* __restrict__ U, const float* __restrict__ xy, int C, int H,
+// kC > 0: channel count known at compile time (images: 3) -> the channel loop unrolls and all gathers of a pixel
+// are in flight together; kC == 0: any channel count
+template <int kC>
+__global__ void __launch_bounds__(kThreads) caffe_warp_fwd_kernel(const float* __restrict__ U, const float* __restrict__ xy, int Crt, int H,
                                                                  int W, float* __restrict__ out) {
+  const int C = kC > 0 ? kC : Crt;
   const int n = blockIdx.y, HW = H * W, idx = blockIdx.x * kThreads + threadIdx.x;
   if (idx >= HW) return;
-  const float xx = xy[((size_t)n * 2 + 0) * HW + idx], yy = xy[((size_t)n * 2 + 1) * HW + idx];
+  const float xx = ld_stream(xy + ((size_t)n * 2 + 0) * HW + idx), yy = ld_stream(xy + ((size_t)n * 2 + 1) * HW + idx);
   const float fx1 = floorf(xx), fy1 = floorf(yy);
   const int x1 = __float2int_rz(fx1), x2 = x1 + 1, y1 = __float2int_rz(fy1), y2 = y1 + 1;
   const float wx2 = sub(xx, (float)x1), wx1 = sub((float)x2, xx), wy2 = sub(yy, (float)y1), wy1 = sub((float)y2, yy);
   const bool bx1 = (unsigned)x1 < (unsigned)W, bx2 = (unsigned)x2 < (unsigned)W, by1 = (unsigned)y1 < (unsigned)H, by2 = (unsigned)y2 < (unsigned)H;
+  const bool p11 = bx1 && by1, p12 = bx1 && by2, p21 = bx2 && by1, p22 = bx2 && by2;
+  const float w11 = mul(wx1, wy1), w12 = mul(wx1, wy2), w21 = mul(wx2, wy1), w22 = mul(wx2, wy2);
+  const float* pl = U + (size_t)n * C * HW + x1 + y1 * W;     // only dereferenced under the predicates
+  float* o = out + (size_t)n * C * HW + idx;
+#pragma unroll
   for (int c = 0; c < C; ++c) {
-    const float* pl = U + ((size_t)n * C + c) * HW;
+    const float u11 = p11 ? __ldg(pl) : 0.0f, u12 = p12 ? __ldg(pl + W) : 0.0f;
+    const float u21 = p21 ? __ldg(pl + 1) : 0.0f, u22 = p22 ? __ldg(pl + W + 1) : 0.0f;
     float v = 0.0f;   // += w_x * w_y * U, in the reference's tap order
-    if (bx1 && by1) v = add(v, mul(mul(wx1, wy1), __ldg(pl + x1 + y1 * W)));
-    if (bx1 && by2) v = add(v, mul(mul(wx1, wy2), __ldg(pl + x1 + y2 * W)));
-    if (bx2 && by1) v = add(v, mul(mul(wx2, wy1), __ldg(pl + x2 + y1 * W)));
-    if (bx2 && by2) v = add(v, mul(mul(wx2, wy2), __ldg(pl + x2 + y2 * W)));
-    out[((size_t)n * C + c) * HW + idx] = v;
+    v = p11 ? add(v, mul(w11, u11)) : v;
+    v = p12 ? add(v, mul(w12, u12)) : v;
+    v = p21 ? add(v, mul(w21, u21)) : v;
+    v = p22 ? add(v, mul(w22, u22)) : v;
+    st_stream(o, v);
+    pl += HW;
+    o += HW;
   }
 }
 
+template <int kC, bool kDiffU>
 __global__ void __launch_bounds__(kThreads) caffe_warp_bwd_kernel(const float* __restrict__ top, const float* __restrict__ U,
-                                                                 const float* __restrict__ xy, int C, int H, int W,
+                                                                 const float* __restrict__ xy, int Crt, int H, int W,
                                                                  float* __restrict__ U_diff, float* __restrict__ xy_diff) {
+  const int C = kC > 0 ? kC : Crt;
   const int n = blockIdx.y, HW = H * W, idx = blockIdx.x * kThreads + threadIdx.x;
   if (idx >= HW) return;
   const size_t ox = ((size_t)n * 2 + 0) * HW + idx, oy = ((size_t)n * 2 + 1) * HW + idx;
-  const float xx = xy[ox], yy = xy[oy];
+  const float xx = ld_stream(xy + ox), yy = ld_stream(xy + oy);
   const int x1 = __float2int_rz(floorf(xx)), x2 = x1 + 1, y1 = __float2int_rz(floorf(yy)), y2 = y1 + 1;
   const float wx2 = sub(xx, (float)x1), wx1 = sub((float)x2, xx), wy2 = sub(yy, (float)y1), wy1 = sub((float)y2, yy);
   const bool bx1 = (unsigned)x1 < (unsigned)W, bx2 = (unsigned)x2 < (unsigned)W, by1 = (unsigned)y1 < (unsigned)H, by2 = (unsigned)y2 < (unsigned)H;
+  const bool p11 = bx1 && by1, p12 = bx1 && by2, p21 = bx2 && by1, p22 = bx2 && by2;
   float tl = 0.0f, tr = 0.0f, bl = 0.0f, br = 0.0f;
+  const size_t tap = (size_t)n * C * HW + x1 + y1 * W;
+  const float* pl = U + tap;
+  const float* gt = top + (size_t)n * C * HW + idx;
+#pragma unroll
   for (int c = 0; c < C; ++c) {
-    const size_t off = ((size_t)n * C + c) * HW;
-    const float g = top[off + idx];
-    if (bx1 && by1) { if (U_diff) atomicAdd(U_diff + off + x1 + y1 * W, mul(mul(g, wx1), wy1)); tl = add(tl, mul(g, __ldg(U + off + W * y1 + x1))); }
-    if (bx1 && by2) { if (U_diff) atomicAdd(U_diff + off + x1 + y2 * W, mul(mul(g, wx1), wy2)); bl = add(bl, mul(g, __ldg(U + off + W * y2 + x1))); }
-    if (bx2 && by1) { if (U_diff) atomicAdd(U_diff + off + x2 + y1 * W, mul(mul(g, wx2), wy1)); tr = add(tr, mul(g, __ldg(U + off + W * y1 + x2))); }
-    if (bx2 && by2) { if (U_diff) atomicAdd(U_diff + off + x2 + y2 * W, mul(mul(g, wx2), wy2)); br = add(br, mul(g, __ldg(U + off + W * y2 + x2))); }
+    const float g = ld_stream(gt);
+    const float u11 = p11 ? __ldg(pl) : 0.0f, u12 = p12 ? __ldg(pl + W) : 0.0f;
+    const float u21 = p21 ? __ldg(pl + 1) : 0.0f, u22 = p22 ? __ldg(pl + W + 1) : 0.0f;
+    tl = p11 ? add(tl, mul(g, u11)) : tl;
+    bl = p12 ? add(bl, mul(g, u12)) : bl;
+    tr = p21 ? add(tr, mul(g, u21)) : tr;
+    br = p22 ? add(br, mul(g, u22)) : br;
+    if (kDiffU) {
+      float* gu = U_diff + tap + (size_t)c * HW;
+      if (p11) atomicAdd(gu, mul(mul(g, wx1), wy1));
+      if (p12) atomicAdd(gu + W, mul(mul(g, wx1), wy2));
+      if (p21) atomicAdd(gu + 1, mul(mul(g, wx2), wy1));
+      if (p22) atomicAdd(gu + W + 1, mul(mul(g, wx2), wy2));
+    }
+    pl += HW;
+    gt += HW;
   }
   if (xy_diff) {
-    xy_diff[ox] = add(mul(sub(tr, tl), wy1), mul(sub(br, bl), wy2));
-    xy_diff[oy] = add(mul(sub(bl, tl), wx1), mul(sub(br, tr), wx2));
+    st_stream(xy_diff + ox, add(mul(sub(tr, tl), wy1), mul(sub(br, bl), wy2)));
+    st_stream(xy_diff + oy, add(mul(sub(bl, tl), wx1), mul(sub(br, tr), wx2)));
   }
 }
 
@@ -228,7 +261,8 @@ DVF_EXPORT int dvf_caffe_geo_bwd(const float* top, const float* depth, const flo
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   if (T_diff) cudaMemsetAsync(T_diff, 0, sizeof(float) * 16 * N, cs);
   if (K_diff) cudaMemsetAsync(K_diff, 0, sizeof(float) * 4 * N, cs);
-  caffe_geo_bwd_kernel<<<grid_of(N, H * W), kThreads, 0, cs>>>(top, depth, T, K, H, W, depth_diff, T_diff, K_diff);
+  const dim3 grid((H * W + kThreads * kGeoBwdPx - 1) / (kThreads * kGeoBwdPx), N);
+  caffe_geo_bwd_kernel<<<grid, kThreads, 0, cs>>>(top, depth, T, K, H, W, depth_diff, T_diff, K_diff);
   return launch_status();
 }
 
@@ -252,7 +286,9 @@ DVF_EXPORT int dvf_caffe_pinhole_bwd(const float* coords_diff, const float* pts,
 DVF_EXPORT int dvf_caffe_warp_fwd(const float* img, const float* coords, int32_t N, int32_t C, int32_t H, int32_t W, float* out, void* stream) {
   if (!img || !coords || !out) return DVF_EINVAL_NULL;
   if (bad_nhw(N, H, W) || C <= 0) return DVF_EINVAL_SHAPE;
-  caffe_warp_fwd_kernel<<<grid_of(N, H * W), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(img, coords, C, H, W, out);
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  if (C == 3) caffe_warp_fwd_kernel<3><<<grid_of(N, H * W), kThreads, 0, cs>>>(img, coords, C, H, W, out);
+  else caffe_warp_fwd_kernel<0><<<grid_of(N, H * W), kThreads, 0, cs>>>(img, coords, C, H, W, out);
   return launch_status();
 }
 
@@ -262,7 +298,11 @@ DVF_EXPORT int dvf_caffe_warp_bwd(const float* top, const float* img, const floa
   if (bad_nhw(N, H, W) || C <= 0) return DVF_EINVAL_SHAPE;
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   if (img_diff) cudaMemsetAsync(img_diff, 0, sizeof(float) * (size_t)N * C * H * W, cs);
-  caffe_warp_bwd_kernel<<<grid_of(N, H * W), kThreads, 0, cs>>>(top, img, coords, C, H, W, img_diff, coords_diff);
+  const dim3 grid = grid_of(N, H * W);
+  if (C == 3 && img_diff) caffe_warp_bwd_kernel<3, true><<<grid, kThreads, 0, cs>>>(top, img, coords, C, H, W, img_diff, coords_diff);
+  else if (C == 3) caffe_warp_bwd_kernel<3, false><<<grid, kThreads, 0, cs>>>(top, img, coords, C, H, W, img_diff, coords_diff);
+  else if (img_diff) caffe_warp_bwd_kernel<0, true><<<grid, kThreads, 0, cs>>>(top, img, coords, C, H, W, img_diff, coords_diff);
+  else caffe_warp_bwd_kernel<0, false><<<grid, kThreads, 0, cs>>>(top, img, coords, C, H, W, img_diff, coords_diff);
   return launch_status();
 }
 
