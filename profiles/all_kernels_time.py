@@ -12,7 +12,7 @@ a = ap.parse_args()
 peak = a.peak
 if not peak:
     try:
-        peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbps"]["burst"])
+        peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         peak = 6545.0
 dev = torch.device("cuda"); B, C, H, W = a.batch, 3, bench.H, bench.W; HW = H * W
