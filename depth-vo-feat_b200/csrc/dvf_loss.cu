@@ -20,6 +20,11 @@ struct Plan {
   int iters[DVF_MAX_LEVELS];
   int block_begin[DVF_MAX_LEVELS];
   int total_blocks;
+  // image kernel (balanced split, dvf_loss_kernel.cuh): 256-pixel units, image-major
+  int units_per_image[DVF_MAX_LEVELS], unit_base[DVF_MAX_LEVELS], slots_c3[DVF_MAX_LEVELS];
+  long long total_units;
+  int units_per_image_all, piece_overhead;
+  int max_ctas_c3;
   size_t off_partials[DVF_MAX_LEVELS], off_terms[DVF_MAX_LEVELS], off_cnt[DVF_MAX_LEVELS], off_lcnt[DVF_MAX_LEVELS];
   size_t off_gM, off_pcnt;
   size_t bytes;
@@ -51,6 +56,31 @@ static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) 
   int iters = (int)(total_px / (chunk * want_blocks));
   if (iters < 1) iters = 1;
   if (iters > 64) iters = 64;
+  // image kernel: every resident CTA slot gets an equal share of the 256-pixel units of the launch.  The grid is
+  // decided at launch time (occupancy of the variant); the partial-sum slots are sized for the largest one.
+  pl.max_ctas_c3 = 8 * num_sms();
+  {
+    const char* e = getenv("DVF_PIECE_OVERHEAD");   // tuning aid
+    pl.piece_overhead = (e && atoi(e) >= 0) ? atoi(e) : 4;   // measured: 0 -> 81.9 us, 3 -> 71.9, 4 -> 69.5, 6 -> 71.4 on C2
+  }
+  long long per_image = 0;
+  for (int l = 0; l < d->n_levels; ++l) {
+    const long long HW = (long long)levels[l].H * levels[l].W;
+    pl.units_per_image[l] = (int)((HW + kUnitPx - 1) / kUnitPx);
+    pl.unit_base[l] = (int)per_image;
+    per_image += pl.units_per_image[l] + pl.piece_overhead;
+  }
+  pl.units_per_image_all = (int)per_image;
+  pl.total_units = per_image * d->B;
+  if (pl.total_units >= (1ll << 31)) return DVF_EINVAL_SHAPE;
+  for (int l = 0; l < d->n_levels; ++l) {
+    // an image of U units is cut by at most ceil(U / floor(T/G)) + 1 CTAs, and by at most U of them
+    const long long G = pl.total_units < pl.max_ctas_c3 ? pl.total_units : pl.max_ctas_c3;
+    const long long per = pl.total_units / G;   // >= 1
+    long long slots = (pl.units_per_image[l] + per - 1) / per + 1;
+    if (slots > pl.units_per_image[l]) slots = pl.units_per_image[l];
+    pl.slots_c3[l] = (int)slots;
+  }
   size_t off = 0;
   int begin = 0;
   for (int l = 0; l < d->n_levels; ++l) {
@@ -63,7 +93,8 @@ static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) 
     pl.block_begin[l] = begin;
     begin += pl.blocks_per_image[l] * d->B;
     pl.off_partials[l] = off;
-    off += align_up((size_t)pl.blocks_per_image[l] * d->B * d->V * kRedSlots * sizeof(float), 256);
+    const int slots = pl.blocks_per_image[l] > pl.slots_c3[l] ? pl.blocks_per_image[l] : pl.slots_c3[l];
+    off += align_up((size_t)slots * d->B * d->V * kRedSlots * sizeof(float), 256);
     pl.off_terms[l] = off;
     off += align_up((size_t)d->B * d->V * sizeof(double), 256);
     pl.off_cnt[l] = off;
@@ -105,6 +136,8 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     const int vec = bf16 ? 8 : 4;
     const int lpp = d->C / vec;
     if (d->C % vec != 0 || lpp < 1 || lpp > 32 || (lpp & (lpp - 1)) != 0) return DVF_EUNSUPPORTED;   // C = vec * 2^k
+    for (int l = 0; l < d->n_levels; ++l)   // the kernel addresses one image with 32-bit byte offsets
+      if ((long long)levels[l].H * levels[l].W * d->C * 4 >= (1ll << 31)) return DVF_EUNSUPPORTED;
   }
   if (d->padding != DVF_PAD_ZEROS && d->padding != DVF_PAD_BORDER) return DVF_EINVAL_DTYPE;
   if (!workspace || workspace_bytes < pl.bytes) return DVF_EWORKSPACE;
@@ -170,6 +203,9 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     t.blocks_per_image = pl.blocks_per_image[l];
     t.iters = pl.iters[l];
     t.px_per_cta = pl.iters[l] * kPlanUnit;
+    t.slots_per_image = pl.blocks_per_image[l];
+    t.unit_base = pl.unit_base[l];
+    t.units_per_image = pl.units_per_image[l];
     t.partials = reinterpret_cast<float*>(ws + pl.off_partials[l]);
     t.img_terms = reinterpret_cast<double*>(ws + pl.off_terms[l]);
     t.img_counter = reinterpret_cast<unsigned*>(ws + pl.off_cnt[l]);
@@ -179,7 +215,10 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
   prm.gM_ws = reinterpret_cast<double*>(ws + pl.off_gM);
   prm.pose_counter = reinterpret_cast<unsigned*>(ws + pl.off_pcnt);
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
-  const int nb = pl.total_blocks;
+  prm.total_units = (int)pl.total_units;
+  prm.units_per_image_all = pl.units_per_image_all;
+  prm.piece_overhead = pl.piece_overhead;
+  int nb = pl.total_blocks;
 #define DVF_DISPATCH_V(FN, Z)                                  \
   switch (d->V) {                                              \
     case 1: FN<1, Z>(prm, nb, cs); break;                      \
@@ -198,6 +237,9 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     if (zeros) { DVF_DISPATCH_NHWC(true) } else { DVF_DISPATCH_NHWC(false) }
 #undef DVF_DISPATCH_NHWC
   } else if (uses_c3_kernel(d, levels)) {
+    // balanced split: the launcher picks the grid (resident CTAs of the variant, at most max_ctas_c3)
+    for (int l = 0; l < d->n_levels; ++l) prm.lv[l].slots_per_image = pl.slots_c3[l];
+    nb = pl.max_ctas_c3;
     bool expl = false;
     for (int l = 0; l < d->n_levels; ++l) expl |= (levels[l].expl != nullptr);
     for (int l = 0; l < d->n_levels; ++l)

@@ -5,11 +5,11 @@ namespace dvf {
 template <int kV, bool kZeros, bool kTma>
 static void launch_loss_c3_t(const LossParams& prm, int blocks, bool expl, bool grad, cudaStream_t st) {
   if (expl) {
-    if (grad) photo_loss_c3x2_kernel<kV, kZeros, true, true, kTma><<<blocks, kLossThreads, 0, st>>>(prm);
-    else photo_loss_c3x2_kernel<kV, kZeros, true, false, kTma><<<blocks, kLossThreads, 0, st>>>(prm);
+    if (grad) launch_balanced<photo_loss_c3x2_kernel<kV, kZeros, true, true, kTma>>(prm, blocks, st);
+    else launch_balanced<photo_loss_c3x2_kernel<kV, kZeros, true, false, kTma>>(prm, blocks, st);
   } else {
-    if (grad) photo_loss_c3x2_kernel<kV, kZeros, false, true, kTma><<<blocks, kLossThreads, 0, st>>>(prm);
-    else photo_loss_c3x2_kernel<kV, kZeros, false, false, kTma><<<blocks, kLossThreads, 0, st>>>(prm);
+    if (grad) launch_balanced<photo_loss_c3x2_kernel<kV, kZeros, false, true, kTma>>(prm, blocks, st);
+    else launch_balanced<photo_loss_c3x2_kernel<kV, kZeros, false, false, kTma>>(prm, blocks, st);
   }
 }
 template <int kV, bool kZeros>

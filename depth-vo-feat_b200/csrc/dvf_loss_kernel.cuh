@@ -16,6 +16,8 @@
 //     butterfly, then per CTA, and the LAST CTA of an image (atomic ticket) adds the CTA partials in
 //     a fixed order in fp64 -> deterministic, no output needs pre-zeroing, no second launch.
 #pragma once
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "dvf_internal.h"
@@ -50,7 +52,13 @@ struct LevelDev {
   float* gP;
   int block_begin, blocks_per_image, iters;
   int px_per_cta;         // contiguous target pixels owned by one CTA (multiple of kPlanUnit)
-  float* partials;        // [B*blocks_per_image][V][kRedSlots]
+  // balanced (persistent) split of the image kernel: the launch is a list of 256-pixel units, image-major, then
+  // level, then position, each (image, level) preceded by `piece_overhead` empty units that stand for its fixed
+  // cost; CTA c of G owns units [c*T/G, (c+1)*T/G) and may cross level and image boundaries
+  int unit_base;          // offset of this level inside an image's unit list (including the overhead units)
+  int units_per_image;    // 256-pixel units of one image of this level
+  int slots_per_image;    // partial-sum slots reserved per image (>= CTAs that can touch one image)
+  float* partials;        // [B*slots_per_image][V][kRedSlots]
   double* img_terms;      // [B][V]
   unsigned* img_counter;  // [B]   zero between launches
   unsigned* lvl_counter;  // [1]   zero between launches
@@ -59,6 +67,9 @@ struct LevelDev {
 struct LossParams {
   int n_levels, B, C, V;
   int need_grad, rotation;
+  int total_units;         // balanced split: units of the launch = B * units_per_image_all
+  int units_per_image_all; // units of one image over all levels, overhead units included
+  int piece_overhead;      // empty units in front of every (image, level)
   float* terms;  // [n_levels*V]
   // pose mode (dvf_photo_loss_fused_pose): P / K^-1_s are derived in the CTA prologue, d pose in the epilogue
   const float* pose_vec;   // [B,V,6] or nullptr
@@ -165,10 +176,12 @@ __device__ __forceinline__ float signed_unit(float d, float inv_n, bool gate) {
   return nz ? copysignf(inv_n, d) : 0.0f;
 }
 
-// Shared tail of both kernels: CTA fold of acc[kV][16], partial write, ticket, image fold, level fold.
+// Shared tail of the loss kernels: CTA fold of acc[kV][16], partial write, ticket, image fold, level fold.
+// `part` of `n_parts`: which of the CTA pieces of image b this is (fixed fold order => deterministic sums).
+// Does not return early: the image kernel calls it once per piece of its unit range.
 template <int kV, int kThreadsT>
 __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], const LossParams& prm, const LevelDev& lv,
-                                                  int l, int rel, int b, int C) {
+                                                  int l, int part, int n_parts, int b, int C) {
   __shared__ float s_red[kThreadsT / 32][kV][kRedSlots];
   __shared__ int s_flag;
   __shared__ double s_term[kThreadsT / 32];
@@ -180,7 +193,8 @@ __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], c
     if ((lane & 1) == 0) s_red[warp][v][butterfly_slot(lane)] = r;
   }
   __syncthreads();
-  float* my_part = lv.partials + (size_t)rel * kV * kRedSlots;
+  float* const img_part = lv.partials + (size_t)b * lv.slots_per_image * kV * kRedSlots;
+  float* const my_part = img_part + (size_t)part * kV * kRedSlots;
   if (tid < kV * kRedSlots) {
     const int v = tid / kRedSlots, s = tid % kRedSlots;
     float t = 0.0f;
@@ -190,97 +204,97 @@ __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], c
     __threadfence();   // only the writers need to publish
   }
   __syncthreads();
-  if (tid == 0) s_flag = (atomicAdd(lv.img_counter + b, 1u) == (unsigned)(lv.blocks_per_image - 1));
+  if (tid == 0) s_flag = (atomicAdd(lv.img_counter + b, 1u) == (unsigned)(n_parts - 1));
   __syncthreads();
-  if (!s_flag) return;
-
-  // ---- last CTA of image b: fixed-order fp64 fold of the CTA partials ----------------
-  __threadfence();
-  const float* img_part = lv.partials + (size_t)b * lv.blocks_per_image * kV * kRedSlots;
-  for (int pair = tid >> 3; pair < kV * kRedSlots; pair += kThreadsT / 8) {
-    const int v = pair / kRedSlots, s = pair % kRedSlots;
-    const double sum = group8_sum(img_part + v * kRedSlots + s, lv.blocks_per_image, kV * kRedSlots, tid & 7);
-    if ((tid & 7) == 0) {
-      if (s < 12) {
-        if (lv.gP) lv.gP[((size_t)b * kV + v) * 12 + s] = (float)sum;
-        s_gp[v][s] = (float)sum;
-      } else if (s == 12) {
-        lv.img_terms[(size_t)b * kV + v] = sum;
-      }
-    }
-  }
-  __threadfence();
-  __syncthreads();
-  if (prm.gvec) {
-    // pose mode: dL/d pose_mat of this level = K_s^T @ dL/dP (fp64); the level that finishes LAST for image b
-    // adds the levels in fixed order and runs the analytic backward of pose_vec2mat
-    if (tid < kV) {
-      level_gM(prm.K + b * 9, lv.ds, &s_gp[tid][0], prm.gM_ws + (((size_t)l * prm.B + b) * kV + tid) * 12);
-      __threadfence();
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const bool last_level = atomicAdd(prm.pose_counter + b, 1u) == (unsigned)(prm.n_levels - 1);
-      if (last_level) prm.pose_counter[b] = 0u;
-      s_flag = last_level;
-    }
-    __syncthreads();
-    if (s_flag) {
-      // this sits at the tail of the kernel: spread it over threads instead of one long fp64 chain per view
-      __threadfence();
-      __shared__ double s_gM[kV][12];
-      __shared__ double s_dtrig[kV][6];
-      const bool euler = prm.rotation == DVF_ROT_EULER;
-      if (tid < kV * 12) {
-        const int v = tid / 12, q = tid % 12;
-        double s = 0.0;
-        for (int ll = 0; ll < prm.n_levels; ++ll) s += __ldcg(prm.gM_ws + (((size_t)ll * prm.B + b) * kV + v) * 12 + q);
-        s_gM[v][q] = s;
-      } else if (euler && tid >= 64 && tid < 64 + kV * 6) {
-        const int v = (tid - 64) / 6, q = (tid - 64) % 6;        // q: 0 sx, 1 cx, 2 sy, 3 cy, 4 sz, 5 cz
-        s_dtrig[v][q] = dtrig_of((double)prm.pose_vec[((size_t)b * kV + v) * 6 + 3 + q / 2], q & 1);
-      }
-      __syncthreads();
-      if (tid < kV * 6) {
-        const int v = tid / 6, q = tid % 6;
-        float* gv = prm.gvec + ((size_t)b * kV + v) * 6;
-        if (q < 3) {
-          gv[q] = (float)s_gM[v][q * 4 + 3];                      // translation: last column of dL/d pose_mat
-        } else if (euler) {
-          gv[q] = euler_angle_grad(&s_gM[v][0], &s_dtrig[v][0], q - 3);
-        } else if (q == 3) {
-          float g6[6];
-          posemat_bwd(&s_gM[v][0], prm.pose_vec + ((size_t)b * kV + v) * 6, prm.rotation, g6);
-          gv[3] = g6[3]; gv[4] = g6[4]; gv[5] = g6[5];
+  if (s_flag) {   // CTA-uniform
+    // ---- last piece of image b: fixed-order fp64 fold of the partials ----------------
+    __threadfence();
+    for (int pair = tid >> 3; pair < kV * kRedSlots; pair += kThreadsT / 8) {
+      const int v = pair / kRedSlots, s = pair % kRedSlots;
+      const double sum = group8_sum(img_part + v * kRedSlots + s, n_parts, kV * kRedSlots, tid & 7);
+      if ((tid & 7) == 0) {
+        if (s < 12) {
+          if (lv.gP) lv.gP[((size_t)b * kV + v) * 12 + s] = (float)sum;
+          s_gp[v][s] = (float)sum;
+        } else if (s == 12) {
+          lv.img_terms[(size_t)b * kV + v] = sum;
         }
       }
     }
+    __threadfence();
     __syncthreads();
-  }
-  if (tid == 0) {
-    lv.img_counter[b] = 0u;
-    s_flag = (atomicAdd(lv.lvl_counter, 1u) == (unsigned)(prm.B - 1));
-  }
-  __syncthreads();
-  if (!s_flag) return;
-
-  // ---- last image of the level: loss terms ---------------------------------------------
-  __threadfence();
-  for (int v = 0; v < kV; ++v) {
-    double s = 0.0;
-    for (int bb = tid; bb < prm.B; bb += kThreadsT) s += __ldcg(lv.img_terms + (size_t)bb * kV + v);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) s_term[warp] = s;
-    __syncthreads();
+    if (prm.gvec) {
+      // pose mode: dL/d pose_mat of this level = K_s^T @ dL/dP (fp64); the level that finishes LAST for image b
+      // adds the levels in fixed order and runs the analytic backward of pose_vec2mat
+      if (tid < kV) {
+        level_gM(prm.K + b * 9, lv.ds, &s_gp[tid][0], prm.gM_ws + (((size_t)l * prm.B + b) * kV + tid) * 12);
+        __threadfence();
+      }
+      __syncthreads();
+      if (tid == 0) {
+        const bool last_level = atomicAdd(prm.pose_counter + b, 1u) == (unsigned)(prm.n_levels - 1);
+        if (last_level) prm.pose_counter[b] = 0u;
+        s_flag = last_level;
+      }
+      __syncthreads();
+      if (s_flag) {
+        // this sits at the tail of the kernel: spread it over threads instead of one long fp64 chain per view
+        __threadfence();
+        __shared__ double s_gM[kV][12];
+        __shared__ double s_dtrig[kV][6];
+        const bool euler = prm.rotation == DVF_ROT_EULER;
+        if (tid < kV * 12) {
+          const int v = tid / 12, q = tid % 12;
+          double s = 0.0;
+          for (int ll = 0; ll < prm.n_levels; ++ll) s += __ldcg(prm.gM_ws + (((size_t)ll * prm.B + b) * kV + v) * 12 + q);
+          s_gM[v][q] = s;
+        } else if (euler && tid >= 64 && tid < 64 + kV * 6) {
+          const int v = (tid - 64) / 6, q = (tid - 64) % 6;        // q: 0 sx, 1 cx, 2 sy, 3 cy, 4 sz, 5 cz
+          s_dtrig[v][q] = dtrig_of((double)prm.pose_vec[((size_t)b * kV + v) * 6 + 3 + q / 2], q & 1);
+        }
+        __syncthreads();
+        if (tid < kV * 6) {
+          const int v = tid / 6, q = tid % 6;
+          float* gv = prm.gvec + ((size_t)b * kV + v) * 6;
+          if (q < 3) {
+            gv[q] = (float)s_gM[v][q * 4 + 3];                      // translation: last column of dL/d pose_mat
+          } else if (euler) {
+            gv[q] = euler_angle_grad(&s_gM[v][0], &s_dtrig[v][0], q - 3);
+          } else if (q == 3) {
+            float g6[6];
+            posemat_bwd(&s_gM[v][0], prm.pose_vec + ((size_t)b * kV + v) * 6, prm.rotation, g6);
+            gv[3] = g6[3]; gv[4] = g6[4]; gv[5] = g6[5];
+          }
+        }
+      }
+      __syncthreads();
+    }
     if (tid == 0) {
-      double t = 0.0;
-      for (int w8 = 0; w8 < kThreadsT / 32; ++w8) t += s_term[w8];
-      prm.terms[l * kV + v] = (float)(t / ((double)prm.B * (double)C * (double)lv.HW));
+      lv.img_counter[b] = 0u;
+      s_flag = (atomicAdd(lv.lvl_counter, 1u) == (unsigned)(prm.B - 1));
     }
     __syncthreads();
+    if (s_flag) {
+      // ---- last image of the level: loss terms ---------------------------------------------
+      __threadfence();
+      for (int v = 0; v < kV; ++v) {
+        double s = 0.0;
+        for (int bb = tid; bb < prm.B; bb += kThreadsT) s += __ldcg(lv.img_terms + (size_t)bb * kV + v);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) s_term[warp] = s;
+        __syncthreads();
+        if (tid == 0) {
+          double t = 0.0;
+          for (int w8 = 0; w8 < kThreadsT / 32; ++w8) t += s_term[w8];
+          prm.terms[l * kV + v] = (float)(t / ((double)prm.B * (double)C * (double)lv.HW));
+        }
+        __syncthreads();
+      }
+      if (tid == 0) *lv.lvl_counter = 0u;
+    }
   }
-  if (tid == 0) *lv.lvl_counter = 0u;
+  __syncthreads();   // s_flag / s_red may be rewritten by the caller's next piece
 }
 
 // ================================================================================================
@@ -297,8 +311,14 @@ __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], c
 // kernel is otherwise limited by how many loads its warps can have outstanding.  Requires HW % 4 == 0 and
 // 16-byte aligned tensors (checked on the host); otherwise the same kernel runs with plain loads.
 // ================================================================================================
-constexpr int kPlanUnit = 512;   // granularity (pixels) of the host's work split; multiple of every kernel's chunk
+constexpr int kPlanUnit = 512;   // granularity (pixels) of the host's work split for the generic / NHWC kernels
+constexpr int kUnitPx = 2 * kLossThreads;   // image kernel: one unit = one pixel pair per thread of the CTA
 constexpr int kStages = 4;
+
+// CTA that owns global unit g when CTA c owns [floor(c*T/G), floor((c+1)*T/G))
+__device__ __forceinline__ int cta_of_unit(int g, int G, int T) {
+  return (int)((((long long)g + 1) * G - 1) / T);
+}
 
 template <int kV, bool kZeros, bool kExpl, bool kGrad, bool kTma, int kMinBlocks = 4>
 __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kernel(const __grid_constant__ LossParams prm) {
@@ -307,8 +327,7 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   // pixel pairs per thread between two ring hand-overs: 2 halves the CTA barriers; with masks the ring would get
   // too shallow (measured: 71 vs 75 us without masks, 151 vs 145 us with masks at V=2)
   constexpr int kPairsPerChunk = kPlanes <= 4 ? 2 : 1;
-  constexpr int kChunk = 2 * kLossThreads * kPairsPerChunk;    // pixels per chunk
-  static_assert(kPlanUnit % kChunk == 0, "plan unit must be a multiple of the chunk");
+  constexpr int kChunk = kUnitPx * kPairsPerChunk;    // pixels per chunk
   // ring depth: as deep as 40 KB of static shared memory allow (4 CTAs per SM stay resident), at least 2
   constexpr int kStagesFit = 40000 / (kPlanes * kChunk * 4);
   constexpr int kSt = kStagesFit >= kStages ? kStages : (kStagesFit < 2 ? 2 : kStagesFit);
@@ -317,24 +336,39 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   __shared__ __align__(128) float s_ring[kTma ? kSt : 1][kTma ? kPlanes : 1][kTma ? kChunk : 4];
   __shared__ __align__(8) uint64_t s_full[kSt];
 
-  int l = 0;
-  while (l + 1 < prm.n_levels && (int)blockIdx.x >= prm.lv[l + 1].block_begin) ++l;
-  const LevelDev& lv = prm.lv[l];
-  const int rel = (int)blockIdx.x - lv.block_begin;
-  const int b = rel / lv.blocks_per_image;
-  const int chunk = rel - b * lv.blocks_per_image;
   const int tid = threadIdx.x;
-  const int H = lv.H, W = lv.W, HW = lv.HW;
-  const Geo geo = lv.geo;
-  const Geo2 geo2 = make_geo2(geo);
-  const FastDiv divW = lv.divW;
-  const float inv_n = lv.inv_n;
-
   if (kTma && tid == 0) {
 #pragma unroll
     for (int s = 0; s < kSt; ++s) mbar_init(&s_full[s], 1);
     mbar_fence_init();
   }
+
+  // balanced split: this CTA owns units [w, w_end) of the launch-wide unit list; it walks them (image, level) by
+  // (image, level) -- "pieces", each with its own matrices, accumulators and partial-sum slot
+  const int G = (int)gridDim.x, T = prm.total_units;
+  int w = (int)((long long)blockIdx.x * T / G);
+  const int w_end = (int)(((long long)blockIdx.x + 1) * T / G);
+  int ring_k = 0;   // chunks this CTA has pushed through the ring so far (stage / parity bookkeeping)
+
+  while (w < w_end) {
+  const int b = w / prm.units_per_image_all;
+  int l = 0;
+  while (l + 1 < prm.n_levels && w - b * prm.units_per_image_all >= prm.lv[l + 1].unit_base) ++l;
+  const LevelDev& lv = prm.lv[l];
+  const int real0 = b * prm.units_per_image_all + lv.unit_base + prm.piece_overhead;   // first pixel-carrying unit
+  const int real1 = real0 + lv.units_per_image;
+  const int piece_end = min(w_end, real1);
+  const int k0 = max(w, real0) - real0, k1 = piece_end - real0;   // units [k0, k1) of image b at level l
+  w = piece_end;
+  if (k1 <= k0) continue;   // only overhead units fell into my range (CTA-uniform)
+  const int first_cta = cta_of_unit(real0, G, T);
+  const int n_parts = cta_of_unit(real1 - 1, G, T) - first_cta + 1;
+  const int part = (int)blockIdx.x - first_cta;
+  const int H = lv.H, W = lv.W, HW = lv.HW;
+  const Geo geo = lv.geo;
+  const Geo2 geo2 = make_geo2(geo);
+  const FastDiv divW = lv.divW;
+  const float inv_n = lv.inv_n;
 
   f2 acc2[kV][12];     // dL/dP partial sums, (A,B) lanes folded at the end
   float accl[kV];      // loss partial sums
@@ -355,16 +389,16 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
 #pragma unroll
   for (int v = 0; v < kV; ++v) src_b[v] = lv.src[v] + (size_t)b * kC * HW;
 
-  // this CTA owns pixels [px_begin, px_end) of image b (host plan), walked in chunks of kChunk
-  const int px_begin = chunk * lv.px_per_cta;
-  const int px_end = min(px_begin + lv.px_per_cta, HW);
+  // this piece: pixels [px_begin, px_end) of image b, walked in chunks of kChunk (the last one may be short)
+  const int px_begin = k0 * kUnitPx;
+  const int px_end = min(k1 * kUnitPx, HW);
   const int n_chunks = (px_end - px_begin + kChunk - 1) / kChunk;
 
   // producer (thread 0): bulk copies of chunk k into ring stage k % kStages + L2 prefetch of the source rows
   auto issue = [&](int k) {
     const int start = px_begin + k * kChunk;
     const uint32_t bytes = (uint32_t)(min(kChunk, px_end - start) * 4);   // multiple of 16 (HW % 4 == 0)
-    const int st = k % kSt;
+    const int st = (ring_k + k) % kSt;
     mbar_expect_tx(&s_full[st], bytes * kPlanes);
     bulk_g2s(&s_ring[st][0][0], depth_b + start, bytes, &s_full[st]);
 #pragma unroll
@@ -413,17 +447,19 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   // one chunk; kTail = the chunk may contain lanes past the end of the run (only the last chunk can)
   auto do_chunk = [&](int k, auto tail_tag) {
     constexpr bool kTail = decltype(tail_tag)::value;
-    if (kTma) mbar_wait(&s_full[k % kSt], (uint32_t)(k / kSt) & 1u);
+    const int st = (ring_k + k) % kSt;
+    if (kTma) mbar_wait(&s_full[st], (uint32_t)((ring_k + k) / kSt) & 1u);
+    // a short last chunk (the unit granularity is one pair per thread) has fewer pairs
+    const int n_pairs = kPairsPerChunk == 1 ? 1 : min(kPairsPerChunk, (px_end - (px_begin + k * kChunk) + kUnitPx - 1) / kUnitPx);
 #pragma unroll 1
-    for (int h = 0; h < kPairsPerChunk; ++h) {
-    const int slot = h * (2 * kLossThreads) + 2 * tid;          // my pair inside the chunk
+    for (int h = 0; h < n_pairs; ++h) {
+    const int slot = h * kUnitPx + 2 * tid;          // my pair inside the chunk
     const int idxA = px_begin + k * kChunk + slot;
     const int idxB = idxA + 1;
     const bool liveA = !kTail || idxA < px_end, liveB = !kTail || idxB < px_end;
     f2 dep, tg0, tg1, tg2;
     f2 exv[kExpl ? kV : 1];
     if (kTma) {
-      const int st = k % kSt;
       dep = *reinterpret_cast<const f2*>(&s_ring[st][0][slot]);
       tg0 = *reinterpret_cast<const f2*>(&s_ring[st][1][slot]);
       tg1 = *reinterpret_cast<const f2*>(&s_ring[st][2][slot]);
@@ -445,7 +481,18 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
     }
     // dead lanes (past the end of the run) may read stale ring contents: give them a harmless depth; their
     // taps are never loaded (all-zero => invalid => zero gradients) and nothing of theirs is stored
-    if (kTail) dep = make_float2(liveA ? dep.x : 1.0f, liveB ? dep.y : 1.0f);
+    if (kTail) {
+      dep = make_float2(liveA ? dep.x : 1.0f, liveB ? dep.y : 1.0f);
+      // ... and finite target / weight values: stale shared memory may hold NaNs of an earlier kernel, and 0 * NaN
+      // would reach the dL/dP sums through the (zero) gradient of a dead lane
+      tg0 = make_float2(liveA ? tg0.x : 0.0f, liveB ? tg0.y : 0.0f);
+      tg1 = make_float2(liveA ? tg1.x : 0.0f, liveB ? tg1.y : 0.0f);
+      tg2 = make_float2(liveA ? tg2.x : 0.0f, liveB ? tg2.y : 0.0f);
+      if (kExpl) {
+#pragma unroll
+        for (int v = 0; v < kV; ++v) exv[v] = make_float2(liveA ? exv[v].x : 1.0f, liveB ? exv[v].y : 1.0f);
+      }
+    }
     Cam2 cam;
     {
       const int ca = kTail ? min(idxA, HW - 1) : idxA, cb = kTail ? min(idxB, HW - 1) : idxB;
@@ -601,9 +648,10 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   };
   for (int k = 0; k + 1 < n_chunks; ++k) do_chunk(k, std::false_type{});
   if (n_chunks > 0) {
-    if (px_end - px_begin == n_chunks * kChunk) do_chunk(n_chunks - 1, std::false_type{});
-    else do_chunk(n_chunks - 1, std::true_type{});
+    if ((px_end - px_begin) % kUnitPx == 0) do_chunk(n_chunks - 1, std::false_type{});
+    else do_chunk(n_chunks - 1, std::true_type{});   // ragged end of the image: lanes past it are predicated off
   }
+  ring_k += n_chunks;
 
   float acc[kV][kRedSlots];
 #pragma unroll
@@ -613,7 +661,8 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
     acc[v][12] = accl[v];
     acc[v][13] = acc[v][14] = acc[v][15] = 0.0f;
   }
-  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, rel, b, kC);
+  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, part, n_parts, b, kC);
+  }  // pieces of this CTA
 }
 
 // ================================================================================================
@@ -753,7 +802,25 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_cn_kernel(const __
     }
     if (need_grad && live && lv.gdepth) st_stream(lv.gdepth + (size_t)b * HW + idx, gd);
   }
-  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, rel, b, C);
+  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, chunk, lv.blocks_per_image, b, C);
+}
+
+// Launch of the image kernel: one CTA per resident slot of this variant (occupancy query, cached per variant), every
+// CTA an equal share of the units => a single wave without a tail.  DVF_CTAS_PER_SM overrides (tuning aid).
+template <void (*kKernel)(const LossParams)>
+inline void launch_balanced(const LossParams& prm, int cap, cudaStream_t st) {
+  static int per_sm = 0;   // benign race: every thread computes the same value
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kKernel, kLossThreads, 0) != cudaSuccess || n < 1) n = 1;
+    const char* e = getenv("DVF_CTAS_PER_SM");
+    if (e && atoi(e) > 0) n = atoi(e);
+    per_sm = n;
+  }
+  long long g = (long long)per_sm * num_sms();
+  if (g > cap) g = cap;
+  if (g > prm.total_units) g = prm.total_units;
+  kKernel<<<(int)g, kLossThreads, 0, st>>>(prm);
 }
 
 template <int kV, bool kZeros>

@@ -7,7 +7,7 @@
 // a texel is contiguous), the validity mask / d(ix,iy) sums are sub-warp shuffle reductions, the target-map
 // gradient is a plain vector store and the source-map gradient scatter is ONE vector reduction per lane and
 // tap (red.global.add.v4.f32, sm_90+) instead of 4*C scalar atomics per pixel.  The coordinate chain is the
-// scalar exact one (dvf_math.cuh), evaluated redundantly by the lanes of a group.
+// scalar exact one (dvf_math.cuh), evaluated once per pixel by an owner lane and broadcast to the group.
 // Arithmetic is fp32 throughout; bf16 inputs are widened on load (geometry stays fp32), gradients to the maps
 // are produced in fp32 NHWC buffers.
 #pragma once
@@ -17,23 +17,20 @@
 
 namespace dvf {
 
+// one 16-byte vector of a texel's channels: 4 fp32 or 8 bf16 values per lane, loaded raw and widened at use
 template <bool kBf16>
 struct VecIO;
 template <>
-struct VecIO<false> {   // 4 fp32 channels per lane
+struct VecIO<false> {
   static constexpr int kVec = 4;
-  static __device__ __forceinline__ void load(const void* base, size_t elem, bool pred, float (&v)[4]) {
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pred) t = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(base) + elem));
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  static __device__ __forceinline__ void widen(const uint4& t, float (&v)[4]) {
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
   }
 };
 template <>
-struct VecIO<true> {    // 8 bf16 channels per lane
+struct VecIO<true> {
   static constexpr int kVec = 8;
-  static __device__ __forceinline__ void load(const void* base, size_t elem, bool pred, float (&v)[8]) {
-    uint4 t = make_uint4(0u, 0u, 0u, 0u);
-    if (pred) t = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(base) + elem));
+  static __device__ __forceinline__ void widen(const uint4& t, float (&v)[8]) {
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {   // bf16 -> fp32 is a 16-bit shift
@@ -42,15 +39,74 @@ struct VecIO<true> {    // 8 bf16 channels per lane
     }
   }
 };
+// 16 bytes at base + byte_off (32-bit offset inside one image: ONE wide multiply-add per address), zeros if !pred
+__device__ __forceinline__ uint4 ld_vec16(const char* base, int byte_off, unsigned pred) {
+  uint4 t = make_uint4(0u, 0u, 0u, 0u);
+  // predicated load INTO the zeroed registers (written in PTX: the C form makes nvcc load into temporaries and
+  // copy them over under the predicate, four extra instructions per tap)
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 a;\n"
+      "setp.ne.u32 p, %6, 0;\n"
+      "mad.wide.s32 a, %5, 1, %4;\n"
+      "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [a];\n"
+      "}\n"
+      : "+r"(t.x), "+r"(t.y), "+r"(t.z), "+r"(t.w)
+      : "l"(base), "r"(byte_off), "r"(pred));
+  return t;
+}
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// 16-byte vector reduction at base + byte_off, executed under `pred` (a predicated instruction, not a branch)
+__device__ __forceinline__ void red_add_v4(char* base, int byte_off, unsigned pred, float a, float b, float c, float d) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 a;\n"
+      "setp.ne.u32 p, %6, 0;\n"
+      "mad.wide.s32 a, %1, 1, %0;\n"
+      "@p red.global.add.v4.f32 [a], {%2, %3, %4, %5};\n"
+      "}\n" ::"l"(base), "r"(byte_off), "f"(a), "f"(b), "f"(c), "f"(d), "r"(pred)
+      : "memory");
+}
+
+// sums of (x, y[, z]) over aligned groups of kLanes lanes: straight-line xor butterfly (same order as a loop over
+// q = 1, 2, 4, ...: results are bit-identical for every group size)
+template <int kLanes>
+__device__ __forceinline__ void group_sum(float& x, float& y, float& z, bool with_z) {
+#pragma unroll
+  for (int q = 1; q < kLanes; q <<= 1) {
+    x += __shfl_xor_sync(0xffffffffu, x, q);
+    y += __shfl_xor_sync(0xffffffffu, y, q);
+    if (with_z) z += __shfl_xor_sync(0xffffffffu, z, q);
+  }
+}
+__device__ __forceinline__ void group_sum_dispatch(int lpp_shift, float& x, float& y, float& z, bool with_z) {
+  switch (lpp_shift) {   // warp-uniform
+    case 0: break;
+    case 1: group_sum<2>(x, y, z, with_z); break;
+    case 2: group_sum<4>(x, y, z, with_z); break;
+    case 3: group_sum<8>(x, y, z, with_z); break;
+    case 4: group_sum<16>(x, y, z, with_z); break;
+    default: group_sum<32>(x, y, z, with_z); break;
+  }
 }
 
 // C = lanes_per_px * kVec;  lanes_per_px in {1,2,4,8,16,32}
+//
+// A warp walks its share of the CTA's pixel run 32 pixels at a time, in three phases:
+//   A  every lane OWNS one of the 32 pixels and evaluates the exact coordinate chain for it once per view
+//      (pixel2cam, cam2pixel, bilinear cell) -- not once per lane of the channel group as before, which made
+//      the kernel instruction-bound (9.5 k thread-instructions per warped pixel at C = 64);
+//   B  the warp then visits the pixels 32/lpp at a time: the cell (offset, tap predicates, weights, mask weight)
+//      is broadcast from the owner lane by shuffles, every lane handles its kVec channels of all four taps,
+//      the value-based mask and the d(ix,iy) sums are folded over the group, the source-map gradient leaves as
+//      one 16-byte reduction per lane and tap, and the folded sums are shuffled back to the owner;
+//   C  the owner lanes run the backward of the coordinate chain for their pixel (depth gradient, dL/dP sums).
 template <int kV, bool kZeros, bool kBf16>
 __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const __grid_constant__ LossParams prm) {
   constexpr int kVec = VecIO<kBf16>::kVec;
+  constexpr unsigned kFull = 0xffffffffu;
   __shared__ __align__(16) float s_P[kV][12];
   __shared__ __align__(16) float s_M[12];
 
@@ -60,11 +116,14 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
   const int rel = (int)blockIdx.x - lv.block_begin;
   const int b = rel / lv.blocks_per_image;
   const int chunk = rel - b * lv.blocks_per_image;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = lv.H, W = lv.W, HW = lv.HW, C = prm.C;
-  const int lpp = C / kVec;                 // lanes per pixel
-  const int slot = lane & (lpp - 1);        // my slot in the group
-  const int ch0 = slot * kVec;               // my first channel
+  const int lpp = C / kVec;                 // lanes per pixel (power of two)
+  const int lpp_shift = __ffs(lpp) - 1;
+  const int pps = 32 >> lpp_shift;          // pixels the warp handles per step
+  const int grp = lane >> lpp_shift;        // my channel group
+  const int ch0 = (lane & (lpp - 1)) * kVec;   // my first channel
+  const unsigned grp_mask = lpp == 32 ? 0xffffffffu : ((1u << lpp) - 1u);
   const Geo geo = lv.geo;
   const bool need_grad = prm.need_grad != 0;
   const bool allow_fast = lv.allow_fast != 0;
@@ -79,32 +138,44 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
   for (int v = 0; v < kV; ++v)
 #pragma unroll
     for (int k = 0; k < kRedSlots; ++k) acc[v][k] = 0.0f;
-  float M[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) M[k] = s_M[k];
 
   const size_t img_px = (size_t)b * HW;     // pixel offset of this image; element offset = px * C
   const float* depth_b = lv.depth + img_px;
+  // per-image bases; inside an image every byte offset fits 32 bits (HW * C * 4 < 2^31, checked on the host)
+  constexpr int kEsz = kBf16 ? 2 : 4;
+  const char* const tgt_b = static_cast<const char*>(static_cast<const void*>(lv.tgt)) + img_px * C * kEsz;
+  const char* src_bb[kV];
+  float* gsrc_b[kV];
+#pragma unroll
+  for (int v = 0; v < kV; ++v) {
+    src_bb[v] = static_cast<const char*>(static_cast<const void*>(lv.src[v])) + img_px * C * kEsz;
+    gsrc_b[v] = lv.gsrc[v] ? lv.gsrc[v] + img_px * C : nullptr;
+    asm volatile("" : "+l"(src_bb[v]), "+l"(gsrc_b[v]));   // keep the bases in registers (nvcc re-derives them per load otherwise)
+  }
   float* gtgt_b = lv.gtgt ? lv.gtgt + img_px * C : nullptr;
-  const int px_per_iter = kLossThreads / lpp;
+  const char* tgt_bb = tgt_b;
+  asm volatile("" : "+l"(tgt_bb), "+l"(gtgt_b));
+  const int row_b = W * C * kEsz, px_b = C * kEsz, ch_b = ch0 * kEsz;   // byte strides of the maps
   const int px_begin = chunk * lv.px_per_cta;
   const int px_end = min(px_begin + lv.px_per_cta, HW);
 
-  for (int base = px_begin; base < px_end; base += px_per_iter) {
-    const int idx = base + tid / lpp;
+  for (int base = px_begin + warp * 32; base < px_end; base += kLossThreads) {
+    // ---- phase A: my own pixel -------------------------------------------------------------------
+    const int idx = base + lane;
     const bool live = idx < px_end;
     const int idc = live ? idx : px_end - 1;
     Cam cam;
     {
+      float M[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) M[k] = s_M[k];
       const int i = (int)fastdiv((uint32_t)idc, lv.divW);
       pixel_to_cam(M, ld_stream(depth_b + idc), i, idc - i * W, cam);
     }
-    float tg[kVec], gt[kVec];
-    VecIO<kBf16>::load(lv.tgt, (img_px + idc) * C + ch0, live, tg);
-#pragma unroll
-    for (int c = 0; c < kVec; ++c) gt[c] = 0.0f;
-    float gd = 0.0f;
-
+    int c_off[kV];          // y0 * W + x0 of the cell (only dereferenced under the tap predicates)
+    unsigned c_pk[kV];      // tap predicates nw | ne << 1 | sw << 2 | se << 3, false for pixels past the run
+    float c_w[kV], c_e[kV], c_n[kV], c_s[kV], c_ex[kV];
+    float r_gx[kV], r_gy[kV], r_ge[kV];   // folded sums coming back from phase B
 #pragma unroll
     for (int v = 0; v < kV; ++v) {
       float P[12];
@@ -115,62 +186,130 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
       const bool fast = project<false, kZeros>(P, cam, geo, pr) && allow_fast;
       if (__builtin_expect(!fast, 0)) pr = project_exact<kZeros>(&s_P[v][0], cam, &lv.geo);
       locate<kZeros>(pr.xn, pr.yn, H, W, geo, L);
-      const bool bnw = L.bnw && live, bne = L.bne && live, bsw = L.bsw && live, bse = L.bse && live;
-      const size_t o_nw = (img_px + (size_t)(L.y0 * W + L.x0)) * C + ch0;     // only dereferenced under the tap predicates
-      float a0[kVec], a1[kVec], a2[kVec], a3[kVec];
-      VecIO<kBf16>::load(lv.src[v], o_nw, bnw, a0);
-      VecIO<kBf16>::load(lv.src[v], o_nw + C, bne, a1);
-      VecIO<kBf16>::load(lv.src[v], o_nw + (size_t)W * C, bsw, a2);
-      VecIO<kBf16>::load(lv.src[v], o_nw + (size_t)W * C + C, bse, a3);
-      const float ex = (has_expl && live) ? ld_stream(lv.expl + (size_t)b * lv.expl_bstride + (size_t)v * HW + idc) : 1.0f;
-      const float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
+      c_off[v] = L.y0 * W + L.x0;
+      c_pk[v] = live ? ((L.bnw ? 1u : 0u) | (L.bne ? 2u : 0u) | (L.bsw ? 4u : 0u) | (L.bse ? 8u : 0u)) : 0u;
+      c_w[v] = L.w; c_e[v] = L.e; c_n[v] = L.n; c_s[v] = L.s;
+      c_ex[v] = (has_expl && live) ? ld_stream(lv.expl + (size_t)b * lv.expl_bstride + (size_t)v * HW + idc) : 1.0f;
+      r_gx[v] = r_gy[v] = r_ge[v] = 0.0f;
+    }
 
-      float d0[kVec], d1[kVec];
-      bool any = false;
+    // ---- phase B: channel work, pps pixels per step ------------------------------------------------
+    for (int s = 0; s < lpp; ++s) {
+      const int p = s * pps + grp;            // owner lane of the pixel my group handles in this step
+      const int pidx = base + p;
+      const bool plive = pidx < px_end;       // uniform over the group
+      const int back = ((lane - s * pps) & (pps - 1)) << lpp_shift;   // owners of this step: lane of "their" group
+      const bool mine = (lane >> (5 - lpp_shift)) == s;
+
+      // every load of the step goes out before any arithmetic: the target vector and the four taps of each view
+      const uint4 raw_t = ld_vec16(tgt_bb, (plive ? pidx : px_end - 1) * px_b + ch_b, plive ? 1u : 0u);
+      uint4 raw[kV][4];
+      int o_b[kV];
+      unsigned pkv[kV];
 #pragma unroll
-      for (int c = 0; c < kVec; ++c) {
-        const float wv = bilerp(a0[c], a1[c], a2[c], a3[c], wnw, wne, wsw, wse);
-        any |= (wv != 0.0f);
-        d0[c] = sub(tg[c], wv);
-        d1[c] = has_expl ? mul(d0[c], ex) : d0[c];
+      for (int v = 0; v < kV; ++v) {
+        o_b[v] = __shfl_sync(kFull, c_off[v], p) * px_b + ch_b;
+        pkv[v] = __shfl_sync(kFull, c_pk[v], p);
+        raw[v][0] = ld_vec16(src_bb[v], o_b[v], pkv[v] & 1u);
+        raw[v][1] = ld_vec16(src_bb[v], o_b[v] + px_b, pkv[v] & 2u);
+        raw[v][2] = ld_vec16(src_bb[v], o_b[v] + row_b, pkv[v] & 4u);
+        raw[v][3] = ld_vec16(src_bb[v], o_b[v] + row_b + px_b, pkv[v] & 8u);
       }
-      // value-based mask over ALL channels of the pixel: OR across the lanes of the group
-      for (int o = 1; o < lpp; o <<= 1) any |= (__shfl_xor_sync(0xffffffffu, (int)any, o) != 0);
-      float lsum = 0.0f;
+      float tg[kVec], gt[kVec];
+      VecIO<kBf16>::widen(raw_t, tg);
 #pragma unroll
-      for (int c = 0; c < kVec; ++c) lsum += fabsf(d1[c]);
-      acc[v][12] += any ? lsum : 0.0f;        // every lane adds its own channels
+      for (int c = 0; c < kVec; ++c) gt[c] = 0.0f;
 
-      if (need_grad) {
-        float gx = 0.0f, gy = 0.0f, ge = 0.0f, g[kVec];
+#pragma unroll
+      for (int v = 0; v < kV; ++v) {
+        Loc L;   // only the weights are used below
+        L.w = __shfl_sync(kFull, c_w[v], p);
+        L.e = __shfl_sync(kFull, c_e[v], p);
+        L.n = __shfl_sync(kFull, c_n[v], p);
+        L.s = __shfl_sync(kFull, c_s[v], p);
+        const float ex = has_expl ? __shfl_sync(kFull, c_ex[v], p) : 1.0f;
+        const unsigned pk = pkv[v];
+        float a0[kVec], a1[kVec], a2[kVec], a3[kVec];
+        VecIO<kBf16>::widen(raw[v][0], a0);
+        VecIO<kBf16>::widen(raw[v][1], a1);
+        VecIO<kBf16>::widen(raw[v][2], a2);
+        VecIO<kBf16>::widen(raw[v][3], a3);
+        const float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
+
+        float d0[kVec], d1[kVec];
+        bool any = false;
 #pragma unroll
         for (int c = 0; c < kVec; ++c) {
-          const float gd1 = signed_unit(d1[c], inv_n, any);
-          g[c] = has_expl ? mul(gd1, ex) : gd1;
-          ge += gd1 * d0[c];
-          gt[c] += g[c];
-          bilerp_grad(a0[c], a1[c], a2[c], a3[c], L, -g[c], gx, gy);
+          const float wv = bilerp(a0[c], a1[c], a2[c], a3[c], wnw, wne, wsw, wse);
+          any |= (wv != 0.0f);
+          d0[c] = sub(tg[c], wv);
+          d1[c] = has_expl ? mul(d0[c], ex) : d0[c];
         }
-        for (int o = 1; o < lpp; o <<= 1) {   // sums over all channels of the pixel
-          gx += __shfl_xor_sync(0xffffffffu, gx, o);
-          gy += __shfl_xor_sync(0xffffffffu, gy, o);
-          ge += __shfl_xor_sync(0xffffffffu, ge, o);
-        }
-        if (lv.gsrc[v] && any) {               // scatter: one 16-byte reduction per tap per kVec/4 quad
-          float* gs = lv.gsrc[v];
+        // value-based mask over ALL channels of the pixel: OR across the lanes of the group (one vote)
+        any = ((__ballot_sync(kFull, any) >> (lane & ~(lpp - 1))) & grp_mask) != 0u;
+        float lsum = 0.0f;
 #pragma unroll
-          for (int q = 0; q < kVec; q += 4) {
-            if (bnw) red_add_v4(gs + o_nw + q, -g[q] * wnw, -g[q + 1] * wnw, -g[q + 2] * wnw, -g[q + 3] * wnw);
-            if (bne) red_add_v4(gs + o_nw + C + q, -g[q] * wne, -g[q + 1] * wne, -g[q + 2] * wne, -g[q + 3] * wne);
-            if (bsw) red_add_v4(gs + o_nw + (size_t)W * C + q, -g[q] * wsw, -g[q + 1] * wsw, -g[q + 2] * wsw, -g[q + 3] * wsw);
-            if (bse) red_add_v4(gs + o_nw + (size_t)W * C + C + q, -g[q] * wse, -g[q + 1] * wse, -g[q + 2] * wse, -g[q + 3] * wse);
+        for (int c = 0; c < kVec; ++c) lsum += fabsf(d1[c]);
+        acc[v][12] += any ? lsum : 0.0f;        // every lane adds its own channels
+
+        if (need_grad) {
+          float gx = 0.0f, gy = 0.0f, ge = 0.0f, g[kVec];
+#pragma unroll
+          for (int c = 0; c < kVec; ++c) {
+            const float gd1 = signed_unit(d1[c], inv_n, any);
+            g[c] = has_expl ? mul(gd1, ex) : gd1;
+            if (has_expl) ge += gd1 * d0[c];
+            gt[c] += g[c];
+            bilerp_grad(a0[c], a1[c], a2[c], a3[c], L, -g[c], gx, gy);
+          }
+          group_sum_dispatch(lpp_shift, gx, gy, ge, has_expl);   // sums over all channels of the pixel
+          if (gsrc_b[v] && any) {               // scatter: one 16-byte reduction per tap per quad of channels
+            const int o_e = kBf16 ? o_b[v] * 2 : o_b[v];   // byte offset in the fp32 gradient map
+            char* const gs = static_cast<char*>(static_cast<void*>(gsrc_b[v]));
+#pragma unroll
+            for (int q = 0; q < kVec; q += 4) {
+              const int oq = o_e + q * 4;
+              red_add_v4(gs, oq, pk & 1u, -g[q] * wnw, -g[q + 1] * wnw, -g[q + 2] * wnw, -g[q + 3] * wnw);
+              red_add_v4(gs, oq + C * 4, pk & 2u, -g[q] * wne, -g[q + 1] * wne, -g[q + 2] * wne, -g[q + 3] * wne);
+              red_add_v4(gs, oq + W * C * 4, pk & 4u, -g[q] * wsw, -g[q + 1] * wsw, -g[q + 2] * wsw, -g[q + 3] * wsw);
+              red_add_v4(gs, oq + W * C * 4 + C * 4, pk & 8u, -g[q] * wse, -g[q + 1] * wse, -g[q + 2] * wse, -g[q + 3] * wse);
+            }
+          }
+          // hand the folded sums to the owner lanes of this step's pixels
+          const float t_gx = __shfl_sync(kFull, gx, back), t_gy = __shfl_sync(kFull, gy, back);
+          const float t_ge = has_expl ? __shfl_sync(kFull, ge, back) : 0.0f;
+          if (mine) {
+            r_gx[v] = t_gx;
+            r_gy[v] = t_gy;
+            r_ge[v] = t_ge;
           }
         }
+      }  // views
+      if (need_grad && plive && gtgt_b) {
+        float* q = gtgt_b + (size_t)pidx * C + ch0;
+#pragma unroll
+        for (int c = 0; c < kVec; c += 4) *reinterpret_cast<float4*>(q + c) = make_float4(gt[c], gt[c + 1], gt[c + 2], gt[c + 3]);
+      }
+    }  // steps
+
+    // ---- phase C: backward of the coordinate chain for my own pixel ------------------------------------
+    if (need_grad) {
+      float gd = 0.0f;
+#pragma unroll
+      for (int v = 0; v < kV; ++v) {
+        float P[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) P[k] = s_P[v][k];
+        Proj pr;
+        Loc L;
+        const bool fast = project<false, kZeros>(P, cam, geo, pr) && allow_fast;   // same values as in phase A
+        if (__builtin_expect(!fast, 0)) pr = project_exact<kZeros>(&s_P[v][0], cam, &lv.geo);
+        locate<kZeros>(pr.xn, pr.yn, H, W, geo, L);
         ChainGrad cg;
-        chain_backward<false>(P, cam, pr, L, gx, gy, geo, cg);
-        if (__builtin_expect(!fast, 0)) cg = chain_backward_exact(&s_P[v][0], cam, pr, L, gx, gy, &lv.geo);
-        if (slot == 0 && live) {               // one lane per pixel owns the per-pixel outputs
-          if (lv.gexpl) st_stream(lv.gexpl + ((size_t)b * kV + v) * HW + idx, ge);
+        chain_backward<false>(P, cam, pr, L, r_gx[v], r_gy[v], geo, cg);
+        if (__builtin_expect(!fast, 0)) cg = chain_backward_exact(&s_P[v][0], cam, pr, L, r_gx[v], r_gy[v], &lv.geo);
+        if (live) {
+          if (lv.gexpl) st_stream(lv.gexpl + ((size_t)b * kV + v) * HW + idx, r_ge[v]);
           gd = add(gd, cg.gdepth);
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
@@ -180,17 +319,10 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
           }
         }
       }
-    }  // views
-    if (need_grad && live) {
-      if (slot == 0 && lv.gdepth) st_stream(lv.gdepth + img_px + idx, gd);
-      if (gtgt_b) {
-        float* q = gtgt_b + (size_t)idx * C + ch0;
-#pragma unroll
-        for (int c = 0; c < kVec; c += 4) *reinterpret_cast<float4*>(q + c) = make_float4(gt[c], gt[c + 1], gt[c + 2], gt[c + 3]);
-      }
+      if (live && lv.gdepth) st_stream(lv.gdepth + img_px + idx, gd);
     }
   }
-  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, rel, b, C);
+  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, chunk, lv.blocks_per_image, b, C);
 }
 
 template <int kV, bool kZeros>
