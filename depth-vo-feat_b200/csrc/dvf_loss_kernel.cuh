@@ -324,9 +324,13 @@ template <int kV, bool kZeros, bool kExpl, bool kGrad, bool kTma, int kMinBlocks
 __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kernel(const __grid_constant__ LossParams prm) {
   constexpr int kC = 3;
   constexpr int kPlanes = 1 + kC + (kExpl ? kV : 0);   // streamed planes per chunk
-  // pixel pairs per thread between two ring hand-overs: 2 halves the CTA barriers; with masks the ring would get
-  // too shallow (measured: 71 vs 75 us without masks, 151 vs 145 us with masks at V=2)
-  constexpr int kPairsPerChunk = kPlanes <= 4 ? 2 : 1;
+  // pixel pairs per thread between two ring hand-overs (= CTA barriers).  Measured on C2 with the balanced split:
+  // 2 pairs x 4 stages 69.6 us, 3 x 3 69.4 us, 4 x 2 67.5 us; with masks the stages get too large for more than 1.
+#ifdef DVF_PAIRS_PER_CHUNK   // experiment builds (profiles/ab.sh)
+  constexpr int kPairsPerChunk = kPlanes <= 4 ? DVF_PAIRS_PER_CHUNK : 1;
+#else
+  constexpr int kPairsPerChunk = kPlanes <= 4 ? 4 : 1;
+#endif
   constexpr int kChunk = kUnitPx * kPairsPerChunk;    // pixels per chunk
   // ring depth: as deep as 40 KB of static shared memory allow (4 CTAs per SM stay resident), at least 2
   constexpr int kStagesFit = 40000 / (kPlanes * kChunk * 4);

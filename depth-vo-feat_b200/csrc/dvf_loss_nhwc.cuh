@@ -103,8 +103,11 @@ __device__ __forceinline__ void group_sum_dispatch(int lpp_shift, float& x, floa
 //      the value-based mask and the d(ix,iy) sums are folded over the group, the source-map gradient leaves as
 //      one 16-byte reduction per lane and tap, and the folded sums are shuffled back to the owner;
 //   C  the owner lanes run the backward of the coordinate chain for their pixel (depth gradient, dL/dP sums).
+#ifndef DVF_NHWC_MINBLOCKS
+#define DVF_NHWC_MINBLOCKS 4
+#endif
 template <int kV, bool kZeros, bool kBf16>
-__global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const __grid_constant__ LossParams prm) {
+__global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_nhwc_kernel(const __grid_constant__ LossParams prm) {
   constexpr int kVec = VecIO<kBf16>::kVec;
   constexpr unsigned kFull = 0xffffffffu;
   __shared__ __align__(16) float s_P[kV][12];
@@ -133,11 +136,19 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
   load_matrices<kV>(prm, lv, b, s_P, s_M);
   __syncthreads();
 
-  float acc[kV][kRedSlots];
+  // Registers are the occupancy limit of this kernel, so the per-pixel state lives in shared memory: the cell of
+  // every owned pixel (phase A -> B), the folded sums going back (B -> C) and the dL/dP sums (per warp).
+  constexpr int kWarps = kLossThreads / 32;
+  __shared__ __align__(16) float s_cell[kWarps][kV][32][8];   // {offset, predicates, w, e}, {n, s, mask weight, -}
+  __shared__ __align__(16) float s_back[kWarps][kV][32][4];   // {sum gx, sum gy, sum ge, -}
+  __shared__ float s_wacc[kWarps][kV][12];
+  float acc_loss[kV];
 #pragma unroll
-  for (int v = 0; v < kV; ++v)
-#pragma unroll
-    for (int k = 0; k < kRedSlots; ++k) acc[v][k] = 0.0f;
+  for (int v = 0; v < kV; ++v) {
+    acc_loss[v] = 0.0f;
+    if (lane < 12) s_wacc[warp][v][lane] = 0.0f;
+  }
+  __syncwarp();
 
   const size_t img_px = (size_t)b * HW;     // pixel offset of this image; element offset = px * C
   const float* depth_b = lv.depth + img_px;
@@ -172,10 +183,6 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
       const int i = (int)fastdiv((uint32_t)idc, lv.divW);
       pixel_to_cam(M, ld_stream(depth_b + idc), i, idc - i * W, cam);
     }
-    int c_off[kV];          // y0 * W + x0 of the cell (only dereferenced under the tap predicates)
-    unsigned c_pk[kV];      // tap predicates nw | ne << 1 | sw << 2 | se << 3, false for pixels past the run
-    float c_w[kV], c_e[kV], c_n[kV], c_s[kV], c_ex[kV];
-    float r_gx[kV], r_gy[kV], r_ge[kV];   // folded sums coming back from phase B
 #pragma unroll
     for (int v = 0; v < kV; ++v) {
       float P[12];
@@ -186,30 +193,33 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
       const bool fast = project<false, kZeros>(P, cam, geo, pr) && allow_fast;
       if (__builtin_expect(!fast, 0)) pr = project_exact<kZeros>(&s_P[v][0], cam, &lv.geo);
       locate<kZeros>(pr.xn, pr.yn, H, W, geo, L);
-      c_off[v] = L.y0 * W + L.x0;
-      c_pk[v] = live ? ((L.bnw ? 1u : 0u) | (L.bne ? 2u : 0u) | (L.bsw ? 4u : 0u) | (L.bse ? 8u : 0u)) : 0u;
-      c_w[v] = L.w; c_e[v] = L.e; c_n[v] = L.n; c_s[v] = L.s;
-      c_ex[v] = (has_expl && live) ? ld_stream(lv.expl + (size_t)b * lv.expl_bstride + (size_t)v * HW + idc) : 1.0f;
-      r_gx[v] = r_gy[v] = r_ge[v] = 0.0f;
+      // y0 * W + x0 of the cell (only dereferenced under the tap predicates nw | ne << 1 | sw << 2 | se << 3, which
+      // are false for pixels past the run)
+      const unsigned pk = live ? ((L.bnw ? 1u : 0u) | (L.bne ? 2u : 0u) | (L.bsw ? 4u : 0u) | (L.bse ? 8u : 0u)) : 0u;
+      const float ex = (has_expl && live) ? ld_stream(lv.expl + (size_t)b * lv.expl_bstride + (size_t)v * HW + idc) : 1.0f;
+      float4* cell = reinterpret_cast<float4*>(&s_cell[warp][v][lane][0]);
+      cell[0] = make_float4(__int_as_float(L.y0 * W + L.x0), __uint_as_float(pk), L.w, L.e);
+      cell[1] = make_float4(L.n, L.s, ex, 0.0f);
     }
+    __syncwarp();
 
     // ---- phase B: channel work, pps pixels per step ------------------------------------------------
     for (int s = 0; s < lpp; ++s) {
       const int p = s * pps + grp;            // owner lane of the pixel my group handles in this step
       const int pidx = base + p;
       const bool plive = pidx < px_end;       // uniform over the group
-      const int back = ((lane - s * pps) & (pps - 1)) << lpp_shift;   // owners of this step: lane of "their" group
-      const bool mine = (lane >> (5 - lpp_shift)) == s;
 
       // every load of the step goes out before any arithmetic: the target vector and the four taps of each view
       const uint4 raw_t = ld_vec16(tgt_bb, (plive ? pidx : px_end - 1) * px_b + ch_b, plive ? 1u : 0u);
       uint4 raw[kV][4];
       int o_b[kV];
       unsigned pkv[kV];
+      float4 cw[kV];   // {offset, predicates, w, e}
 #pragma unroll
       for (int v = 0; v < kV; ++v) {
-        o_b[v] = __shfl_sync(kFull, c_off[v], p) * px_b + ch_b;
-        pkv[v] = __shfl_sync(kFull, c_pk[v], p);
+        cw[v] = *reinterpret_cast<const float4*>(&s_cell[warp][v][p][0]);
+        o_b[v] = __float_as_int(cw[v].x) * px_b + ch_b;
+        pkv[v] = __float_as_uint(cw[v].y);
         raw[v][0] = ld_vec16(src_bb[v], o_b[v], pkv[v] & 1u);
         raw[v][1] = ld_vec16(src_bb[v], o_b[v] + px_b, pkv[v] & 2u);
         raw[v][2] = ld_vec16(src_bb[v], o_b[v] + row_b, pkv[v] & 4u);
@@ -222,12 +232,13 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
 
 #pragma unroll
       for (int v = 0; v < kV; ++v) {
+        const float4 c1 = *reinterpret_cast<const float4*>(&s_cell[warp][v][p][4]);   // {n, s, mask weight, -}
         Loc L;   // only the weights are used below
-        L.w = __shfl_sync(kFull, c_w[v], p);
-        L.e = __shfl_sync(kFull, c_e[v], p);
-        L.n = __shfl_sync(kFull, c_n[v], p);
-        L.s = __shfl_sync(kFull, c_s[v], p);
-        const float ex = has_expl ? __shfl_sync(kFull, c_ex[v], p) : 1.0f;
+        L.w = cw[v].z;
+        L.e = cw[v].w;
+        L.n = c1.x;
+        L.s = c1.y;
+        const float ex = c1.z;
         const unsigned pk = pkv[v];
         float a0[kVec], a1[kVec], a2[kVec], a3[kVec];
         VecIO<kBf16>::widen(raw[v][0], a0);
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
         float lsum = 0.0f;
 #pragma unroll
         for (int c = 0; c < kVec; ++c) lsum += fabsf(d1[c]);
-        acc[v][12] += any ? lsum : 0.0f;        // every lane adds its own channels
+        acc_loss[v] += any ? lsum : 0.0f;       // every lane adds its own channels
 
         if (need_grad) {
           float gx = 0.0f, gy = 0.0f, ge = 0.0f, g[kVec];
@@ -275,14 +286,8 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
               red_add_v4(gs, oq + W * C * 4 + C * 4, pk & 8u, -g[q] * wse, -g[q + 1] * wse, -g[q + 2] * wse, -g[q + 3] * wse);
             }
           }
-          // hand the folded sums to the owner lanes of this step's pixels
-          const float t_gx = __shfl_sync(kFull, gx, back), t_gy = __shfl_sync(kFull, gy, back);
-          const float t_ge = has_expl ? __shfl_sync(kFull, ge, back) : 0.0f;
-          if (mine) {
-            r_gx[v] = t_gx;
-            r_gy[v] = t_gy;
-            r_ge[v] = t_ge;
-          }
+          // hand the folded sums to the owner lane of the pixel
+          if ((lane & (lpp - 1)) == 0) *reinterpret_cast<float4*>(&s_back[warp][v][p][0]) = make_float4(gx, gy, ge, 0.0f);
         }
       }  // views
       if (need_grad && plive && gtgt_b) {
@@ -293,10 +298,12 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
     }  // steps
 
     // ---- phase C: backward of the coordinate chain for my own pixel ------------------------------------
+    __syncwarp();
     if (need_grad) {
       float gd = 0.0f;
 #pragma unroll
       for (int v = 0; v < kV; ++v) {
+        const float4 back = *reinterpret_cast<const float4*>(&s_back[warp][v][lane][0]);
         float P[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) P[k] = s_P[v][k];
@@ -306,21 +313,34 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_nhwc_kernel(const 
         if (__builtin_expect(!fast, 0)) pr = project_exact<kZeros>(&s_P[v][0], cam, &lv.geo);
         locate<kZeros>(pr.xn, pr.yn, H, W, geo, L);
         ChainGrad cg;
-        chain_backward<false>(P, cam, pr, L, r_gx[v], r_gy[v], geo, cg);
-        if (__builtin_expect(!fast, 0)) cg = chain_backward_exact(&s_P[v][0], cam, pr, L, r_gx[v], r_gy[v], &lv.geo);
-        if (live) {
-          if (lv.gexpl) st_stream(lv.gexpl + ((size_t)b * kV + v) * HW + idx, r_ge[v]);
-          gd = add(gd, cg.gdepth);
+        chain_backward<false>(P, cam, pr, L, back.x, back.y, geo, cg);
+        if (__builtin_expect(!fast, 0)) cg = chain_backward_exact(&s_P[v][0], cam, pr, L, back.x, back.y, &lv.geo);
+        if (live && lv.gexpl) st_stream(lv.gexpl + ((size_t)b * kV + v) * HW + idx, back.z);
+        gd = add(gd, live ? cg.gdepth : 0.0f);
+        // dL/dP of the 32 pixels: folded over the warp, added to the warp's sums (one owner lane per entry)
+        float t[kRedSlots];
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
+        for (int r = 0; r < 3; ++r) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) acc[v][r * 4 + k] = fmaf(cg.gq[r], cam.cam[k], acc[v][r * 4 + k]);
-            acc[v][r * 4 + 3] += cg.gq[r];
-          }
+          for (int k = 0; k < 3; ++k) t[r * 4 + k] = live ? cg.gq[r] * cam.cam[k] : 0.0f;
+          t[r * 4 + 3] = live ? cg.gq[r] : 0.0f;
         }
+        t[12] = t[13] = t[14] = t[15] = 0.0f;
+        const float tot = butterfly16(t, lane);
+        const int slot = butterfly_slot(lane);
+        if ((lane & 1) == 0 && slot < 12) s_wacc[warp][v][slot] += tot;
       }
       if (live && lv.gdepth) st_stream(lv.gdepth + img_px + idx, gd);
     }
+  }
+  __syncwarp();
+  float acc[kV][kRedSlots];
+#pragma unroll
+  for (int v = 0; v < kV; ++v) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[v][k] = lane == 0 ? s_wacc[warp][v][k] : 0.0f;
+    acc[v][12] = acc_loss[v];
+    acc[v][13] = acc[v][14] = acc[v][15] = 0.0f;
   }
   reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, chunk, lv.blocks_per_image, b, C);
 }
