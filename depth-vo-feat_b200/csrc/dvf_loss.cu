@@ -60,8 +60,10 @@ static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) 
   // decided at launch time (occupancy of the variant); the partial-sum slots are sized for the largest one.
   pl.max_ctas_c3 = 8 * num_sms();
   {
+    // fixed cost of a piece in units: image kernel measured on C2 0 -> 81.9 us, 3 -> 71.9, 4 -> 69.5, 6 -> 71.4; a unit
+    // of the channels-last kernel is C/kVec times more work, so its pieces cost less than one unit
     const char* e = getenv("DVF_PIECE_OVERHEAD");   // tuning aid
-    pl.piece_overhead = (e && atoi(e) >= 0) ? atoi(e) : 4;   // measured: 0 -> 81.9 us, 3 -> 71.9, 4 -> 69.5, 6 -> 71.4 on C2
+    pl.piece_overhead = (e && atoi(e) >= 0) ? atoi(e) : (d->layout == DVF_NHWC ? 0 : 4);
   }
   long long per_image = 0;
   for (int l = 0; l < d->n_levels; ++l) {
@@ -227,6 +229,8 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     default: FN<4, Z>(prm, nb, cs); break;                     \
   }
   if (nhwc) {
+    for (int l = 0; l < d->n_levels; ++l) prm.lv[l].slots_per_image = pl.slots_c3[l];
+    nb = pl.max_ctas_c3;
 #define DVF_DISPATCH_NHWC(Z)                                        \
   switch (d->V) {                                                   \
     case 1: launch_loss_nhwc<1, Z>(prm, nb, bf16, cs); break;       \

@@ -4,8 +4,8 @@
 namespace dvf {
 template <int kV, bool kZeros>
 void launch_loss_nhwc(const LossParams& prm, int blocks, bool bf16, cudaStream_t st) {
-  if (bf16) photo_loss_nhwc_kernel<kV, kZeros, true><<<blocks, kLossThreads, 0, st>>>(prm);
-  else photo_loss_nhwc_kernel<kV, kZeros, false><<<blocks, kLossThreads, 0, st>>>(prm);
+  if (bf16) launch_balanced<photo_loss_nhwc_kernel<kV, kZeros, true>>(prm, blocks, st);
+  else launch_balanced<photo_loss_nhwc_kernel<kV, kZeros, false>>(prm, blocks, st);
 }
 template void launch_loss_nhwc<1, true>(const LossParams&, int, bool, cudaStream_t);
 template void launch_loss_nhwc<2, true>(const LossParams&, int, bool, cudaStream_t);

@@ -113,22 +113,37 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
   __shared__ __align__(16) float s_P[kV][12];
   __shared__ __align__(16) float s_M[12];
 
-  int l = 0;
-  while (l + 1 < prm.n_levels && (int)blockIdx.x >= prm.lv[l + 1].block_begin) ++l;
-  const LevelDev& lv = prm.lv[l];
-  const int rel = (int)blockIdx.x - lv.block_begin;
-  const int b = rel / lv.blocks_per_image;
-  const int chunk = rel - b * lv.blocks_per_image;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int H = lv.H, W = lv.W, HW = lv.HW, C = prm.C;
+  const int C = prm.C;
   const int lpp = C / kVec;                 // lanes per pixel (power of two)
   const int lpp_shift = __ffs(lpp) - 1;
   const int pps = 32 >> lpp_shift;          // pixels the warp handles per step
   const int grp = lane >> lpp_shift;        // my channel group
   const int ch0 = (lane & (lpp - 1)) * kVec;   // my first channel
   const unsigned grp_mask = lpp == 32 ? 0xffffffffu : ((1u << lpp) - 1u);
-  const Geo geo = lv.geo;
   const bool need_grad = prm.need_grad != 0;
+
+  // balanced split (same unit list and bookkeeping as the image kernel, dvf_loss_kernel.cuh): this CTA owns units
+  // [w, w_end) and walks them (image, level) by (image, level)
+  const int G = (int)gridDim.x, T = prm.total_units;
+  int w = (int)((long long)blockIdx.x * T / G);
+  const int w_end = (int)(((long long)blockIdx.x + 1) * T / G);
+  while (w < w_end) {
+  const int b = w / prm.units_per_image_all;
+  int l = 0;
+  while (l + 1 < prm.n_levels && w - b * prm.units_per_image_all >= prm.lv[l + 1].unit_base) ++l;
+  const LevelDev& lv = prm.lv[l];
+  const int real0 = b * prm.units_per_image_all + lv.unit_base + prm.piece_overhead;   // first pixel-carrying unit
+  const int real1 = real0 + lv.units_per_image;
+  const int piece_end = min(w_end, real1);
+  const int k0 = max(w, real0) - real0, k1 = piece_end - real0;   // units [k0, k1) of image b at level l
+  w = piece_end;
+  if (k1 <= k0) continue;   // only overhead units fell into my range (CTA-uniform)
+  const int first_cta = cta_of_unit(real0, G, T);
+  const int n_parts = cta_of_unit(real1 - 1, G, T) - first_cta + 1;
+  const int part = (int)blockIdx.x - first_cta;
+  const int H = lv.H, W = lv.W, HW = lv.HW;
+  const Geo geo = lv.geo;
   const bool allow_fast = lv.allow_fast != 0;
   const bool has_expl = lv.expl != nullptr;
   const float inv_n = lv.inv_n;
@@ -167,8 +182,8 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
   const char* tgt_bb = tgt_b;
   asm volatile("" : "+l"(tgt_bb), "+l"(gtgt_b));
   const int row_b = W * C * kEsz, px_b = C * kEsz, ch_b = ch0 * kEsz;   // byte strides of the maps
-  const int px_begin = chunk * lv.px_per_cta;
-  const int px_end = min(px_begin + lv.px_per_cta, HW);
+  const int px_begin = k0 * kUnitPx;
+  const int px_end = min(k1 * kUnitPx, HW);
 
   for (int base = px_begin + warp * 32; base < px_end; base += kLossThreads) {
     // ---- phase A: my own pixel -------------------------------------------------------------------
@@ -342,7 +357,8 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
     acc[v][12] = acc_loss[v];
     acc[v][13] = acc[v][14] = acc[v][15] = 0.0f;
   }
-  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, chunk, lv.blocks_per_image, b, C);
+  reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, part, n_parts, b, C);
+  }  // pieces of this CTA
 }
 
 template <int kV, bool kZeros>
