@@ -2,8 +2,9 @@
 // ONE pass over HBM).  See dvf_loss.cu for the host side and the reference citations.
 //
 // One launch covers every pyramid level and every source view of a loss call:
-//   * a CTA owns a contiguous run of target pixels of ONE image of ONE level, so the per-image
-//     projection P and K^-1 are CTA-uniform (kept in shared memory, broadcast reads);
+//   * the launch is a list of 256-pixel units; every resident CTA owns an equal share of it and walks it in
+//     PIECES, contiguous runs of target pixels of ONE image of ONE level, so the per-image projection P and
+//     K^-1 are uniform over a piece (kept in shared memory, broadcast reads);
 //   * each thread owns adjacent pixels of the run, so every depth / target load and depth-gradient store of a
 //     warp is contiguous; in the image kernel these streaming inputs arrive through a TMA-filled ring;
 //   * per pixel the depth / target values are read once and shared by all V views; the 4 bilinear
@@ -13,7 +14,7 @@
 //     the shared-reciprocal divisions are exact (|q| > 2^100, NaN) are redone by a cold out-of-line
 //     routine using __fdiv_rn;
 //   * loss term and the 12 entries of dL/dP are accumulated per thread, folded with a 16-slot
-//     butterfly, then per CTA, and the LAST CTA of an image (atomic ticket) adds the CTA partials in
+//     butterfly, then per piece, and the LAST piece of an image (atomic ticket) adds the partials in
 //     a fixed order in fp64 -> deterministic, no output needs pre-zeroing, no second launch.
 #pragma once
 #include <stdlib.h>
