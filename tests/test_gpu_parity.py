@@ -514,6 +514,42 @@ def test_fused_loss_c3_ragged_shapes_vs_oracle(ops, oracle, syn, B, H, W, V, wit
         assert np.array_equal(npy(t_expl.grad), r["gexpl"])
 
 
+@pytest.mark.parametrize("V,with_expl", [(1, False), (2, True)])
+def test_fused_loss_multi_piece_ctas_vs_oracle(ops, oracle, syn, V, with_expl):
+    """Enough work that every CTA of the balanced split owns several units and crosses image / level boundaries
+    (more units than resident CTAs: pieces, partial-sum slots, ring parity across pieces), against the oracle."""
+    B, H, W, L = 40, 64, 208, 3
+    d = syn.stereo_temporal_batch(B, H, W, seed=91)
+    K, Kinv = d["intrinsics"], d["intrinsics_inv"]
+    sizes = [(H >> s, W >> s) for s in range(L)]
+    ds = [float(1 << s) for s in range(L)]
+    depths = [syn.depth(B, h, w, 92 + i) for i, (h, w) in enumerate(sizes)]
+    expl = [syn.explainability(B, V, h, w, 95 + i) for i, (h, w) in enumerate(sizes)] if with_expl else None
+    pose = torch.stack([d["T_R2L"], d["T_2to1"]][:V], 1)
+    tg = ops.area_pyramid(d["img_R2"].cuda(), sizes)
+    srcs = [ops.area_pyramid(d[n].cuda(), sizes) for n in ["img_L2", "img_R1"][:V]]
+    t_depths = [x.cuda().requires_grad_(True) for x in depths]
+    t_expl = [x.cuda().requires_grad_(True) for x in expl] if with_expl else None
+    t_pose = pose.cuda().requires_grad_(True)
+    loss, terms = ops.fused_photo_loss(tg, [[srcs[v][s] for v in range(V)] for s in range(L)], t_depths, t_pose,
+                                       K.cuda(), Kinv.cuda(), expl_levels=t_expl, downscales=ds)
+    loss.backward()
+    _, P, _ = ops.pose_proj_fwd(t_pose.detach().reshape(B * V, 6), K.cuda(), Kinv.cuda(), V, "euler", ds)
+    gpose = np.zeros((B, V, 6))
+    for s in range(L):
+        Pn = npy(P[s]).reshape(B, V, 3, 4)
+        oK, oKi = oracle.scale_intrinsics(K.numpy(), Kinv.numpy(), ds[s])
+        r = oracle.photo_loss_P(npy(tg[s]), [npy(srcs[v][s]) for v in range(V)], depths[s].numpy(), Pn, oKi,
+                                expl=None if expl is None else expl[s].numpy())
+        assert_close(npy(terms[s * V:(s + 1) * V]), r["terms"], what=f"terms level {s}")
+        assert int((npy(t_depths[s].grad) != r["gdepth"]).sum()) == 0, f"depth gradient level {s} bit-exact"
+        if with_expl:
+            assert_close(npy(t_expl[s].grad), r["gexpl"], what=f"gexpl level {s}")
+        for v in range(V):
+            gpose[:, v] += oracle.pose_bwd(r["gP"][:, v], oK, pose[:, v].numpy())
+    assert_close(npy(t_pose.grad), gpose, what="gpose")
+
+
 def test_fused_loss_forward_only_and_nan_inputs(ops, oracle, syn):
     """no_grad mode runs the loss-only kernel; NaN / huge depths take the exact cold path and propagate like the reference."""
     B, H, W = 2, 24, 80
