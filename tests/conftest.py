@@ -15,6 +15,14 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
+    # DVF_TEST_ORDER=reverse|shuffle:<seed> -- the kernels keep ticket counters in cached workspaces and shared memory
+    # is not cleared between launches, so the suite must pass in any order (it caught a stale-NaN bug once)
+    order = os.environ.get("DVF_TEST_ORDER", "")
+    if order == "reverse":
+        items.reverse()
+    elif order.startswith("shuffle"):
+        import random
+        random.Random(int(order.split(":")[1]) if ":" in order else 0).shuffle(items)
     import torch
     if torch.cuda.is_available():
         return
