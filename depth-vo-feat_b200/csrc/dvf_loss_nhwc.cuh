@@ -39,21 +39,41 @@ struct VecIO<true> {
     }
   }
 };
-// 16 bytes at base + byte_off (32-bit offset inside one image: ONE wide multiply-add per address), zeros if !pred
-__device__ __forceinline__ uint4 ld_vec16(const char* base, int byte_off, unsigned pred) {
+// The channels of a lane.  fp32 maps: 4 consecutive channels (one 16-byte vector).  bf16 maps: TWO groups of 4
+// consecutive channels, C/2 apart (two 8-byte vectors), so that the fp32 gradient of each group is again one 16-byte
+// vector and the lanes of a pixel write contiguous 16-byte pieces -- with 8 consecutive bf16 channels per lane every
+// vector reduction filled only half of each 32-byte sector and the bf16 kernel was slower than the fp32 one.
+// base + byte_off: 32-bit offset inside one image (ONE wide multiply-add per address); zeros if !pred.
+// Predicated load INTO the zeroed registers (written in PTX: the C form makes nvcc load into temporaries and copy
+// them over under the predicate, four extra instructions per tap).
+template <bool kBf16>
+__device__ __forceinline__ uint4 ld_lane_vec(const char* base, int byte_off, int half_b, unsigned pred) {
   uint4 t = make_uint4(0u, 0u, 0u, 0u);
-  // predicated load INTO the zeroed registers (written in PTX: the C form makes nvcc load into temporaries and
-  // copy them over under the predicate, four extra instructions per tap)
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b64 a;\n"
-      "setp.ne.u32 p, %6, 0;\n"
-      "mad.wide.s32 a, %5, 1, %4;\n"
-      "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [a];\n"
-      "}\n"
-      : "+r"(t.x), "+r"(t.y), "+r"(t.z), "+r"(t.w)
-      : "l"(base), "r"(byte_off), "r"(pred));
+  if (kBf16) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 a, b;\n"
+        "setp.ne.u32 p, %7, 0;\n"
+        "mad.wide.s32 a, %5, 1, %4;\n"
+        "mad.wide.s32 b, %6, 1, a;\n"
+        "@p ld.global.nc.v2.u32 {%0, %1}, [a];\n"
+        "@p ld.global.nc.v2.u32 {%2, %3}, [b];\n"
+        "}\n"
+        : "+r"(t.x), "+r"(t.y), "+r"(t.z), "+r"(t.w)
+        : "l"(base), "r"(byte_off), "r"(half_b), "r"(pred));
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 a;\n"
+        "setp.ne.u32 p, %6, 0;\n"
+        "mad.wide.s32 a, %5, 1, %4;\n"
+        "@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [a];\n"
+        "}\n"
+        : "+r"(t.x), "+r"(t.y), "+r"(t.z), "+r"(t.w)
+        : "l"(base), "r"(byte_off), "r"(pred));
+  }
   return t;
 }
 
@@ -119,7 +139,7 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
   const int lpp_shift = __ffs(lpp) - 1;
   const int pps = 32 >> lpp_shift;          // pixels the warp handles per step
   const int grp = lane >> lpp_shift;        // my channel group
-  const int ch0 = (lane & (lpp - 1)) * kVec;   // my first channel
+  const int ch0 = (lane & (lpp - 1)) * 4;      // first channel of my (first) group of 4; bf16: second group at + C/2
   const unsigned grp_mask = lpp == 32 ? 0xffffffffu : ((1u << lpp) - 1u);
   const bool need_grad = prm.need_grad != 0;
 
@@ -181,7 +201,7 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
   float* gtgt_b = lv.gtgt ? lv.gtgt + img_px * C : nullptr;
   const char* tgt_bb = tgt_b;
   asm volatile("" : "+l"(tgt_bb), "+l"(gtgt_b));
-  const int row_b = W * C * kEsz, px_b = C * kEsz, ch_b = ch0 * kEsz;   // byte strides of the maps
+  const int row_b = W * C * kEsz, px_b = C * kEsz, ch_b = ch0 * kEsz, half_b = (C / 2) * kEsz;   // byte strides of the maps
   const int px_begin = k0 * kUnitPx;
   const int px_end = min(k1 * kUnitPx, HW);
 
@@ -225,7 +245,7 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
       const bool plive = pidx < px_end;       // uniform over the group
 
       // every load of the step goes out before any arithmetic: the target vector and the four taps of each view
-      const uint4 raw_t = ld_vec16(tgt_bb, (plive ? pidx : px_end - 1) * px_b + ch_b, plive ? 1u : 0u);
+      const uint4 raw_t = ld_lane_vec<kBf16>(tgt_bb, (plive ? pidx : px_end - 1) * px_b + ch_b, half_b, plive ? 1u : 0u);
       uint4 raw[kV][4];
       int o_b[kV];
       unsigned pkv[kV];
@@ -235,10 +255,10 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
         cw[v] = *reinterpret_cast<const float4*>(&s_cell[warp][v][p][0]);
         o_b[v] = __float_as_int(cw[v].x) * px_b + ch_b;
         pkv[v] = __float_as_uint(cw[v].y);
-        raw[v][0] = ld_vec16(src_bb[v], o_b[v], pkv[v] & 1u);
-        raw[v][1] = ld_vec16(src_bb[v], o_b[v] + px_b, pkv[v] & 2u);
-        raw[v][2] = ld_vec16(src_bb[v], o_b[v] + row_b, pkv[v] & 4u);
-        raw[v][3] = ld_vec16(src_bb[v], o_b[v] + row_b + px_b, pkv[v] & 8u);
+        raw[v][0] = ld_lane_vec<kBf16>(src_bb[v], o_b[v], half_b, pkv[v] & 1u);
+        raw[v][1] = ld_lane_vec<kBf16>(src_bb[v], o_b[v] + px_b, half_b, pkv[v] & 2u);
+        raw[v][2] = ld_lane_vec<kBf16>(src_bb[v], o_b[v] + row_b, half_b, pkv[v] & 4u);
+        raw[v][3] = ld_lane_vec<kBf16>(src_bb[v], o_b[v] + row_b + px_b, half_b, pkv[v] & 8u);
       }
       float tg[kVec], gt[kVec];
       VecIO<kBf16>::widen(raw_t, tg);
@@ -279,6 +299,17 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
         acc_loss[v] += any ? lsum : 0.0f;       // every lane adds its own channels
 
         if (need_grad) {
+          if (kBf16) {
+            // 8 channels per lane: do not keep the 32 widened tap values alive across the vote -- widen them again
+            // from the raw vectors (a shift / a mask each); the empty asm stops the compiler from merging the copies
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              asm volatile("" : "+r"(raw[v][t].x), "+r"(raw[v][t].y), "+r"(raw[v][t].z), "+r"(raw[v][t].w));
+            VecIO<kBf16>::widen(raw[v][0], a0);
+            VecIO<kBf16>::widen(raw[v][1], a1);
+            VecIO<kBf16>::widen(raw[v][2], a2);
+            VecIO<kBf16>::widen(raw[v][3], a3);
+          }
           float gx = 0.0f, gy = 0.0f, ge = 0.0f, g[kVec];
 #pragma unroll
           for (int c = 0; c < kVec; ++c) {
@@ -294,7 +325,7 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
             char* const gs = static_cast<char*>(static_cast<void*>(gsrc_b[v]));
 #pragma unroll
             for (int q = 0; q < kVec; q += 4) {
-              const int oq = o_e + q * 4;
+              const int oq = o_e + (q / 4) * (C / 2) * 4;   // second group of 4 channels: C/2 further
               red_add_v4(gs, oq, pk & 1u, -g[q] * wnw, -g[q + 1] * wnw, -g[q + 2] * wnw, -g[q + 3] * wnw);
               red_add_v4(gs, oq + C * 4, pk & 2u, -g[q] * wne, -g[q + 1] * wne, -g[q + 2] * wne, -g[q + 3] * wne);
               red_add_v4(gs, oq + W * C * 4, pk & 4u, -g[q] * wsw, -g[q + 1] * wsw, -g[q + 2] * wsw, -g[q + 3] * wsw);
@@ -308,7 +339,8 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
       if (need_grad && plive && gtgt_b) {
         float* q = gtgt_b + (size_t)pidx * C + ch0;
 #pragma unroll
-        for (int c = 0; c < kVec; c += 4) *reinterpret_cast<float4*>(q + c) = make_float4(gt[c], gt[c + 1], gt[c + 2], gt[c + 3]);
+        for (int c = 0; c < kVec; c += 4)
+          *reinterpret_cast<float4*>(q + (c / 4) * (C / 2)) = make_float4(gt[c], gt[c + 1], gt[c + 2], gt[c + 3]);
       }
     }  // steps
 
