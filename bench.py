@@ -10,7 +10,8 @@ Workload (BASELINE.json configs[1], SURVEY 8d "C2"): 4-scale stereo photometric 
 per GPU at 128x416 (levels 128x416, 64x208, 32x104, 16x52), one source view (the rectified-stereo pose),
 fp32 NCHW, synthetic KITTI-shaped inputs, image pyramids prebuilt (they are inputs of the path, 8d).
 A step = ONE launch of dvf_photo_loss_fused_pose (pose_vec2mat + projection in the kernel prologue, warp + loss +
-all gradients over all levels, pose backward in the epilogue), replayed from a CUDA graph.  Steps rotate over several distinct input sets whose total size exceeds L2.
+all gradients over all levels, pose backward in the epilogue).  Steps rotate over several distinct input sets whose total
+size exceeds L2; one CUDA graph holds one round of them (--single-step-graphs: one graph per step).
 Multi-GPU: batch sharded, B=64 per rank (weak scaling), no data-path collective; one NCCL all-reduce of the
 loss terms closes the timed region (logging exchange).
 """
@@ -50,6 +51,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
+    ap.add_argument("--single-step-graphs", action="store_true", help="one CUDA graph per step instead of one per round of --sets steps")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--iid-depth", action="store_true", help="stress case: iid-noise depth instead of the smooth field")
@@ -222,12 +224,31 @@ def run_b200(args):
         plans.append(plan)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
+    round_graph = None
     with torch.cuda.stream(side):
         for p in plans:
             graphs.append(p.capture())
             loss_graphs.append(p.capture(loss_only=True))
+        if args.sets > 1 and not args.single_step_graphs:
+            # one graph = one ROUND of `sets` steps (one launch per input set), as a training iteration captured whole
+            # would hold them: consecutive steps are kernel -> kernel edges inside the graph instead of separate graph
+            # launches (~2 us of launch gap per step less).  Still one launch per step, K launches for K steps.
+            round_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(round_graph):
+                for p in plans:
+                    p.launch()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+
+    def run_steps(n, singles):
+        """n steps over the rotating input sets: whole rounds from the round graph, the rest one graph per step"""
+        i = 0
+        if round_graph is not None:
+            for _ in range(n // args.sets):
+                round_graph.replay()
+            i = (n // args.sets) * args.sets
+        for k in range(i, n):
+            singles[k % args.sets].replay()
     wpx_step = plans[0].warped_px
     bytes_launch = plans[0].algorithmic_bytes()
     set_bytes = bytes_launch
@@ -257,8 +278,7 @@ def run_b200(args):
         torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        graphs[i % args.sets].replay()
+    run_steps(args.steps, graphs)
     if world > 1:
         acc_terms.copy_(plans[(args.steps - 1) % args.sets].terms)
         dist.all_reduce(acc_terms)     # the only exchange of the path: <= 16 floats of loss terms
@@ -280,8 +300,7 @@ def run_b200(args):
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     r0.record()
-    for i in range(n_roof):
-        loss_graphs[i % args.sets].replay()
+    run_steps(n_roof, loss_graphs)
     r1.record()
     torch.cuda.synchronize()
     t_load1 = time.time()
@@ -381,7 +400,8 @@ def run_b200(args):
                        "depth_field": "iid-noise (stress)" if args.iid_depth else "smooth (17x17 box-filtered disparity)",
                        "pyramid": "prebuilt inputs (SURVEY 8d)", "parallelism": f"batch-sharded dp{world}",
                        "l2_policy": f"{args.sets} rotating input sets, {args.sets * set_bytes / 1e6:.0f} MB > 126 MB L2",
-                       "step": "CUDA-graph replay of ONE launch: dvf_photo_loss_fused_pose (pose_vec2mat+projection, warp+loss+all gradients over 4 levels, pose backward)"},
+                       "step": "ONE launch: dvf_photo_loss_fused_pose (pose_vec2mat+projection, warp+loss+all gradients over 4 levels, pose backward); "
+                               + ("CUDA graph per step" if round_graph is None else f"CUDA graphs of {args.sets} consecutive steps (one per input set)")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": plans[0].n_launches * args.steps,
             "warped_px_per_step_per_gpu": wpx_step,
