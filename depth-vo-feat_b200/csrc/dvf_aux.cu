@@ -69,9 +69,45 @@ __global__ void __launch_bounds__(kThreads) area_level_kernel(const float* __res
   out[t] = __fdiv_rn(s, (float)((ye - ys) * (xe - xs)));
 }
 
+// ---- layout change of feature maps: dense NCHW -> channels-last (and back) ---------------------------------------
+// The reference hands feature maps over in NCHW (unsupervise.py:104-109); the feature-loss kernel wants a texel's
+// channels contiguous.  Per image this is a [R, S] -> [S, R] transpose (R = C, S = H*W forwards): 32x32 tiles through
+// shared memory, reads coalesced along S, writes coalesced along R.  4 B read + 4 B written per element (HBM bound).
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_tiles_kernel(const T* __restrict__ src, T* __restrict__ dst, int R, int S) {
+  __shared__ T tile[32][33];
+  const size_t img = (size_t)blockIdx.z * R * S;
+  const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int r = r0 + ty + k, sidx = s0 + tx;
+    if (r < R && sidx < S) tile[ty + k][tx] = src[img + (size_t)r * S + sidx];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int sidx = s0 + ty + k, r = r0 + tx;
+    if (r < R && sidx < S) dst[img + (size_t)sidx * R + r] = tile[tx][ty + k];
+  }
+}
+
 }  // namespace dvf
 
 using namespace dvf;
+
+// src [B, R, S] -> dst [B, S, R]; elem_bytes 4 (fp32) or 2 (bf16 / fp16)
+DVF_EXPORT int dvf_transpose_planes(const void* src, void* dst, int32_t B, int32_t R, int32_t S, int32_t elem_bytes, void* stream) {
+  if (!src || !dst) return DVF_EINVAL_NULL;
+  if (B <= 0 || R <= 0 || S <= 0 || B > 65535 || (R + 31) / 32 > 65535) return DVF_EINVAL_SHAPE;
+  if (elem_bytes != 4 && elem_bytes != 2) return DVF_EINVAL_DTYPE;
+  if (!aligned(src, (size_t)elem_bytes) || !aligned(dst, (size_t)elem_bytes)) return DVF_EINVAL_ALIGN;
+  const dim3 grid((unsigned)((S + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B);
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  if (elem_bytes == 4) transpose_tiles_kernel<uint32_t><<<grid, 256, 0, cs>>>(static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst), R, S);
+  else transpose_tiles_kernel<uint16_t><<<grid, 256, 0, cs>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), R, S);
+  return launch_status();
+}
 
 DVF_EXPORT int dvf_area_pyramid(const float* img, int32_t BC, int32_t H, int32_t W, int32_t n_out, float* const* outs,
                                 void* stream) {

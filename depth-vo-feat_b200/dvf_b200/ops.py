@@ -54,9 +54,41 @@ def _nhwc_ok(t: torch.Tensor) -> bool:
     return C_ % vec == 0 and 1 <= lpp <= 32 and (lpp & (lpp - 1)) == 0 and t.data_ptr() % 16 == 0
 
 
+# Feature maps in the reference layout (dense NCHW, what the reference's FeatExtractor hands over, unsupervise.py:104-109)
+# are re-laid out channels-last on the way in when their channel count suits the NHWC kernel: one transpose pass per map
+# buys a 4-7x faster loss kernel (C4 shape: 1.84 ms generic NCHW vs 0.26 ms channels-last).  Their gradients come back
+# as channels-last tensors of the same logical shape.  False: keep NCHW maps on the generic kernel.
+NCHW_FEATURES_VIA_NHWC = True
+
+
+def to_channels_last(t: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] fp32 / bf16 -> the same tensor in channels-last memory (tiled transpose kernel for dense NCHW input;
+    not differentiable: callers take gradients w.r.t. the tensor they passed in)."""
+    if t.is_contiguous(memory_format=torch.channels_last) and not t.is_contiguous():
+        return t
+    src = t.detach()
+    if not src.is_contiguous():
+        return src.contiguous(memory_format=torch.channels_last)
+    B, Cc, H, W = src.shape
+    out = torch.empty_like(src, memory_format=torch.channels_last)
+    _lib.check(_lib.load().dvf_transpose_planes(src.data_ptr(), out.data_ptr(), B, Cc, H * W, src.element_size(), _stream()),
+               "dvf_transpose_planes")
+    return out
+
+
+def _nhwc_candidate(t: torch.Tensor) -> bool:
+    if t.dim() != 4 or t.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    vec = 8 if t.dtype == torch.bfloat16 else 4
+    C_ = t.shape[1]
+    lpp = C_ // vec
+    return C_ >= 8 and C_ % vec == 0 and 1 <= lpp <= 32 and (lpp & (lpp - 1)) == 0
+
+
 def _req_maps(maps, name):
     """Image / feature tensors of one loss call -> (tensors, layout, dtype).  Channels-last fp32 / bf16 maps go to
-    the NHWC kernel as they are; anything else is brought to dense NCHW fp32 (the reference layout)."""
+    the NHWC kernel as they are, dense NCHW feature maps after a re-layout (see NCHW_FEATURES_VIA_NHWC); anything
+    else is brought to dense NCHW fp32 (the reference layout)."""
     for t in maps:
         if not isinstance(t, torch.Tensor):
             raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
@@ -66,6 +98,10 @@ def _req_maps(maps, name):
             raise AssertionError(f"wrong size for {name}, expected 4 dims, got {list(t.size())}")
     if all(_nhwc_ok(t) for t in maps) and len({t.dtype for t in maps}) == 1:
         return list(maps), _lib.NHWC, (_lib.BF16 if maps[0].dtype == torch.bfloat16 else _lib.F32)
+    if NCHW_FEATURES_VIA_NHWC and len({t.dtype for t in maps}) == 1 and all(_nhwc_candidate(t) for t in maps):
+        conv = [t if _nhwc_ok(t) else to_channels_last(t) for t in maps]
+        if all(_nhwc_ok(t) for t in conv):
+            return conv, _lib.NHWC, (_lib.BF16 if conv[0].dtype == torch.bfloat16 else _lib.F32)
     out = []
     for t in maps:
         if t.dtype not in (torch.float32, torch.bfloat16, torch.float16):

@@ -183,6 +183,12 @@ int dvf_area_pyramid(const float* img /*[BC,H,W]*/, int32_t BC, int32_t H, int32
 int dvf_area_downsample(const float* img /*[BC,H,W]*/, int32_t BC, int32_t H, int32_t W,
                         int32_t h, int32_t w, float* out /*[BC,h,w]*/, void* stream);
 
+/* Layout change of feature maps, per image a [R,S] -> [S,R] transpose: dense NCHW -> channels-last with R = C,
+ * S = H*W (the reference's FeatExtractor hands NCHW maps to the loss, unsupervise.py:104-109; the feature-loss
+ * kernel reads channels-last), and back with R = H*W, S = C.  elem_bytes 4 (fp32) or 2 (bf16).               */
+int dvf_transpose_planes(const void* src /*[B,R,S]*/, void* dst /*[B,S,R]*/, int32_t B, int32_t R, int32_t S,
+                         int32_t elem_bytes, void* stream);
+
 /* ---- regularisers next to the path -----------------------
  * smooth_loss (loss_functions.py:23-41, loss_functions_sfm.py:59-77) and explainability_loss
  * (loss_functions_sfm.py:49-56), every scale in ONE launch, value and gradient together.

@@ -129,29 +129,38 @@ def test_fused_loss_single_level_vs_oracle(ops, oracle, syn, V, with_expl, C, pa
     r = oracle.photo_loss_P(tgt.numpy(), [s.numpy() for s in srcs], depth.numpy(), Pn, Kinv.numpy(),
                             expl=None if expl is None else expl.numpy(), padding_mode=pad, need_gsrc=True, need_gtgt=True)
 
-    t_tgt = tgt.cuda().requires_grad_(True)
-    t_srcs = [s.cuda().requires_grad_(True) for s in srcs]
-    t_depth = depth.cuda().requires_grad_(True)
-    t_pose = pose.cuda().requires_grad_(True)
-    t_expl = None if expl is None else expl.cuda().requires_grad_(True)
-    loss, terms = ops.fused_photo_loss([t_tgt], [t_srcs], [t_depth], t_pose, K.cuda(), Kinv.cuda(),
-                                       expl_levels=None if expl is None else [t_expl], padding_mode=pad)
-    loss.backward()
-    # P computed on the GPU may differ from the oracle's in the last place (sin/cos); when it does not,
-    # everything downstream is compared at 1e-5
-    _, P_gpu, _ = ops.pose_proj_fwd(t_pose.detach().reshape(B * V, 6), K.cuda(), None, V, "euler", [1.0])
-    same_P = np.array_equal(npy(P_gpu[0]).reshape(B, V, 3, 4), Pn)
-    tol = RTOL_F32 if same_P else 2e-3
-    assert_close(npy(terms), r["terms"], tol=RTOL_F32, what="loss terms")
-    assert abs(loss.item() - r["terms"].sum()) <= RTOL_F32 * r["terms"].sum()
-    assert_close(npy(t_depth.grad), r["gdepth"], tol=tol, what="gdepth")
-    assert_close(npy(t_tgt.grad), r["gtgt"], tol=tol, what="gtgt")
-    for v in range(V):
-        assert_close(npy(t_srcs[v].grad), r["gsrc"][v], tol=tol, what=f"gsrc{v}")
-        gp = oracle.pose_bwd(r["gP"][:, v], K.numpy(), pose[:, v].numpy())
-        assert_close(npy(t_pose.grad[:, v]), gp, tol=tol, what=f"gpose{v}")
-    if with_expl:
-        assert_close(npy(t_expl.grad), r["gexpl"], tol=tol, what="gexpl")
+    # dense NCHW feature maps reach the channels-last kernel through a re-layout by default; the generic NCHW kernel is
+    # exercised with the switch off
+    for via_nhwc in ([True, False] if feat else [True]):
+        ops.NCHW_FEATURES_VIA_NHWC = via_nhwc
+        try:
+            t_tgt = tgt.cuda().requires_grad_(True)
+            t_srcs = [s.cuda().requires_grad_(True) for s in srcs]
+            t_depth = depth.cuda().requires_grad_(True)
+            t_pose = pose.cuda().requires_grad_(True)
+            t_expl = None if expl is None else expl.cuda().requires_grad_(True)
+            loss, terms = ops.fused_photo_loss([t_tgt], [t_srcs], [t_depth], t_pose, K.cuda(), Kinv.cuda(),
+                                               expl_levels=None if expl is None else [t_expl], padding_mode=pad)
+            loss.backward()
+        finally:
+            ops.NCHW_FEATURES_VIA_NHWC = True
+        # P computed on the GPU may differ from the oracle's in the last place (sin/cos); when it does not,
+        # everything downstream is compared at 1e-5
+        _, P_gpu, _ = ops.pose_proj_fwd(t_pose.detach().reshape(B * V, 6), K.cuda(), None, V, "euler", [1.0])
+        same_P = np.array_equal(npy(P_gpu[0]).reshape(B, V, 3, 4), Pn)
+        tol = RTOL_F32 if same_P else 2e-3
+        what = f" (via_nhwc={via_nhwc})"
+        assert_close(npy(terms), r["terms"], tol=RTOL_F32, what="loss terms" + what)
+        assert abs(loss.item() - r["terms"].sum()) <= RTOL_F32 * r["terms"].sum()
+        assert_close(npy(t_depth.grad), r["gdepth"], tol=tol, what="gdepth" + what)
+        assert t_tgt.grad.shape == t_tgt.shape
+        assert_close(npy(t_tgt.grad), r["gtgt"], tol=tol, what="gtgt" + what)
+        for v in range(V):
+            assert_close(npy(t_srcs[v].grad), r["gsrc"][v], tol=tol, what=f"gsrc{v}" + what)
+            gp = oracle.pose_bwd(r["gP"][:, v], K.numpy(), pose[:, v].numpy())
+            assert_close(npy(t_pose.grad[:, v]), gp, tol=tol, what=f"gpose{v}" + what)
+        if with_expl:
+            assert_close(npy(t_expl.grad), r["gexpl"], tol=tol, what="gexpl" + what)
 
 
 def test_fused_loss_exact_P_path_vs_oracle(ops, oracle, syn):
@@ -449,6 +458,19 @@ def test_feature_loss_channels_last_vs_oracle(ops, oracle, syn, dtype, C, V, wit
                      what=f"gpose{v}")
     if with_expl:
         assert_close(npy(t_expl.grad), r["gexpl"], tol=tol_geo, what="gexpl")
+
+
+@pytest.mark.parametrize("shape,dtype", [((3, 64, 32, 104), torch.float32), ((2, 8, 5, 7), torch.float32),
+                                         ((1, 33, 9, 31), torch.float32), ((2, 64, 32, 104), torch.bfloat16),
+                                         ((1, 16, 3, 5), torch.bfloat16)])
+def test_to_channels_last_matches_torch(ops, shape, dtype):
+    """dvf_transpose_planes behind ops.to_channels_last: a pure re-layout, so the bits must equal torch's."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(*shape, generator=g).to(dtype).cuda()
+    y = ops.to_channels_last(x)
+    assert y.shape == x.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(y, x)
+    assert torch.equal(y.permute(0, 2, 3, 1).contiguous(), x.permute(0, 2, 3, 1).contiguous())
 
 
 def test_regularisers_vs_oracle(ops, oracle, syn):
