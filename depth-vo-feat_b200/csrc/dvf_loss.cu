@@ -60,10 +60,12 @@ static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) 
   // decided at launch time (occupancy of the variant); the partial-sum slots are sized for the largest one.
   pl.max_ctas_c3 = 8 * num_sms();
   {
-    // fixed cost of a piece in units: image kernel measured on C2 0 -> 81.9 us, 3 -> 71.9, 4 -> 69.5, 6 -> 71.4; a unit
-    // of the channels-last kernel is C/kVec times more work, so its pieces cost less than one unit
+    // fixed cost of a piece in units.  Image kernel, measured on C2 (V = 1): 2 -> 73.7 us, 3 -> 69.6, 4 -> 67.4,
+    // 5 -> 67.4, 6 -> 68.5, 8 -> 69.7; with V = 2 a unit is twice the work: 3 -> 120.1 us, 4 -> 122.6, 6 -> 125.4.
+    // A unit of the channels-last kernel is C/kVec times more work again, so its pieces cost less than one unit.
     const char* e = getenv("DVF_PIECE_OVERHEAD");   // tuning aid
-    pl.piece_overhead = (e && atoi(e) >= 0) ? atoi(e) : (d->layout == DVF_NHWC ? 0 : 4);
+    const int by_views = d->V == 1 ? 4 : (d->V == 2 ? 3 : 2);
+    pl.piece_overhead = (e && atoi(e) >= 0) ? atoi(e) : (d->layout == DVF_NHWC ? 0 : by_views);
   }
   long long per_image = 0;
   for (int l = 0; l < d->n_levels; ++l) {
