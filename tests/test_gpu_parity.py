@@ -460,6 +460,55 @@ def test_feature_loss_channels_last_vs_oracle(ops, oracle, syn, dtype, C, V, wit
         assert_close(npy(t_expl.grad), r["gexpl"], tol=tol_geo, what="gexpl")
 
 
+@pytest.mark.parametrize("dtype,C,V,B,sizes,with_expl", [
+    ("f32", 128, 3, 2, [(17, 23)], True),            # 32 lanes per pixel, ragged map, three views
+    ("bf16", 8, 4, 3, [(9, 11)], False),             # one lane per pixel, four views
+    ("f32", 16, 2, 2, [(2, 5)], False),              # two short rows
+    ("f32", 32, 2, 36, [(32, 104), (16, 52)], True),  # two levels, more units than CTAs: multi-piece CTAs
+    ("bf16", 64, 1, 20, [(32, 104), (16, 52), (8, 26)], False),
+])
+def test_feature_loss_channels_last_shapes_vs_oracle(ops, oracle, syn, dtype, C, V, B, sizes, with_expl):
+    """channels-last kernel on awkward shapes (lanes per pixel 1..32, ragged maps, several levels, CTAs that own
+    several pieces) against the oracle, every gradient."""
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    L = len(sizes)
+    H0, W0 = sizes[0]
+    K, Kinv = syn.intrinsics(B, H0, W0)
+    ds = [H0 / h for (h, w) in sizes]
+    kinds = ["kitti", "stereo", "tiny", "large"]
+    pose = torch.stack([syn.pose(B, kinds[v], 31 + v) for v in range(V)], 1)
+    maps = [[m.to(tdt) for m in syn.features(B, C, h, w, 40 + 7 * i, n=V + 1)] for i, (h, w) in enumerate(sizes)]
+    depths = [syn.depth(B, h, w, 50 + i) for i, (h, w) in enumerate(sizes)]
+    expl = [syn.explainability(B, V, h, w, 60 + i) for i, (h, w) in enumerate(sizes)] if with_expl else None
+    cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)   # noqa: E731
+    t_maps = [[cl(m).requires_grad_(True) for m in lv] for lv in maps]
+    t_depths = [d.cuda().requires_grad_(True) for d in depths]
+    t_expl = [e.cuda().requires_grad_(True) for e in expl] if with_expl else None
+    t_pose = pose.cuda().requires_grad_(True)
+    loss, terms = ops.fused_photo_loss([lv[0] for lv in t_maps], [lv[1:] for lv in t_maps], t_depths, t_pose, K.cuda(),
+                                       Kinv.cuda(), expl_levels=t_expl, downscales=ds)
+    loss.backward()
+    _, P, _ = ops.pose_proj_fwd(t_pose.detach().reshape(B * V, 6), K.cuda(), Kinv.cuda(), V, "euler", ds)
+    tol_geo = RTOL_F32 if dtype == "f32" else 1e-4
+    tol_map = RTOL_F32 if dtype == "f32" else 1e-2
+    gpose = np.zeros((B, V, 6))
+    for s in range(L):
+        Pn = npy(P[s]).reshape(B, V, 3, 4)
+        oK, oKi = oracle.scale_intrinsics(K.numpy(), Kinv.numpy(), ds[s])
+        ref = [m.float().numpy() for m in maps[s]]
+        r = oracle.photo_loss_P(ref[0], ref[1:], depths[s].numpy(), Pn, oKi, expl=None if expl is None else expl[s].numpy(),
+                                need_gsrc=True, need_gtgt=True)
+        assert_close(npy(terms[s * V:(s + 1) * V]), r["terms"], tol=tol_geo, what=f"terms level {s}")
+        assert_close(npy(t_depths[s].grad), r["gdepth"], tol=tol_geo, what=f"gdepth level {s}")
+        assert_close(npy(t_maps[s][0].grad.float()), r["gtgt"], tol=tol_map, what=f"gtgt level {s}")
+        for v in range(V):
+            assert_close(npy(t_maps[s][1 + v].grad.float()), r["gsrc"][v], tol=tol_map, what=f"gsrc{v} level {s}")
+            gpose[:, v] += oracle.pose_bwd(r["gP"][:, v], oK, pose[:, v].numpy())
+        if with_expl:
+            assert_close(npy(t_expl[s].grad), r["gexpl"], tol=tol_geo, what=f"gexpl level {s}")
+    assert_close(npy(t_pose.grad), gpose, tol=tol_geo, what="gpose")
+
+
 @pytest.mark.parametrize("shape,dtype", [((3, 64, 32, 104), torch.float32), ((2, 8, 5, 7), torch.float32),
                                          ((1, 33, 9, 31), torch.float32), ((2, 64, 32, 104), torch.bfloat16),
                                          ((1, 16, 3, 5), torch.bfloat16)])
