@@ -34,7 +34,16 @@ struct RegParams {
   float* out;         // [1] loss value
 };
 
-__device__ __forceinline__ float sgnf(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
+// sign(v) in {-1, 0, +1}, 0 for NaN.  The smoothness kernel evaluates 38 of these per 4-pixel strip and is bound by the
+// ALU pipe (compares + selects: 66 % busy against 25 % of the FMA pipe), so the sign is formed on the FMA pipe instead:
+// two saturating multiplies by 2^100 take any non-zero magnitude (down to the smallest denormal, 2^-149) to exactly 1,
+// a NaN saturates to 0.
+__device__ __forceinline__ float sgnf(float v) {
+  const float big = 1.2676506e30f;   // 2^100
+  const float p = __saturatef(__saturatef(v * big) * big);
+  const float n = __saturatef(__saturatef(-v * big) * big);
+  return p - n;
+}
 
 template <typename F>
 __device__ __forceinline__ void finish_scalar(double local, const RegParams& p, F) {
@@ -87,38 +96,59 @@ __device__ __forceinline__ void cross(float m00, float m01, float m10, float m11
   abs_sum = fabsf(dxy) + fabsf(dyx);
 }
 
+// kInterior: the strip and its whole 5 x 8 neighbourhood lie inside the map (the vast majority of strips): no index
+// clamping, every stencil exists -- the border conditions fold away at compile time and the 28 loads are one row
+// pointer each plus constant column offsets.
+template <bool kInterior>
 __device__ __forceinline__ float smooth_strip(const RegLevel& lv, const float* __restrict__ m, float* __restrict__ g, int y, int x) {
   const int H = lv.H, W = lv.W;
   // C[r]: column x, rows y-2..y+5; L1/R1: columns x-1 / x+1, rows y-1..y+4; L2/R2: columns x-2 / x+2, rows y..y+3
   float C[kStrip + 4], L1[kStrip + 2], R1[kStrip + 2], L2[kStrip], R2[kStrip];
-  const int xl1 = max(x - 1, 0), xl2 = max(x - 2, 0), xr1 = min(x + 1, W - 1), xr2 = min(x + 2, W - 1);
+  if (kInterior) {
+    const float* row = m + (y - 2) * W + x;
 #pragma unroll
-  for (int r = 0; r < kStrip + 4; ++r) {
-    const float* row = m + min(max(y + r - 2, 0), H - 1) * W;
-    C[r] = __ldg(row + x);
-    if (r >= 1 && r < kStrip + 3) {
-      L1[r - 1] = __ldg(row + xl1);
-      R1[r - 1] = __ldg(row + xr1);
+    for (int r = 0; r < kStrip + 4; ++r) {
+      C[r] = __ldg(row);
+      if (r >= 1 && r < kStrip + 3) {
+        L1[r - 1] = __ldg(row - 1);
+        R1[r - 1] = __ldg(row + 1);
+      }
+      if (r >= 2 && r < kStrip + 2) {
+        L2[r - 2] = __ldg(row - 2);
+        R2[r - 2] = __ldg(row + 2);
+      }
+      row += W;
     }
-    if (r >= 2 && r < kStrip + 2) {
-      L2[r - 2] = __ldg(row + xl2);
-      R2[r - 2] = __ldg(row + xr2);
+  } else {
+    const int xl1 = max(x - 1, 0), xl2 = max(x - 2, 0), xr1 = min(x + 1, W - 1), xr2 = min(x + 2, W - 1);
+#pragma unroll
+    for (int r = 0; r < kStrip + 4; ++r) {
+      const float* row = m + min(max(y + r - 2, 0), H - 1) * W;
+      C[r] = __ldg(row + x);
+      if (r >= 1 && r < kStrip + 3) {
+        L1[r - 1] = __ldg(row + xl1);
+        R1[r - 1] = __ldg(row + xr1);
+      }
+      if (r >= 2 && r < kStrip + 2) {
+        L2[r - 2] = __ldg(row + xl2);
+        R2[r - 2] = __ldg(row + xr2);
+      }
     }
   }
-  const bool xm2 = x >= 2, xm1 = x >= 1, xp1 = x + 1 < W, xp2 = x + 2 < W;
+  const bool xm2 = kInterior || x >= 2, xm1 = kInterior || x >= 1, xp1 = kInterior || x + 1 < W, xp2 = kInterior || x + 2 < W;
   // dyy anchored at rows y-2 .. y+3 (column x)
   float Dy[kStrip + 2];
 #pragma unroll
   for (int a = 0; a < kStrip + 2; ++a) {
     const int ay = y + a - 2;
-    Dy[a] = (ay >= 0 && ay + 2 < H) ? dd(C[a], C[a + 1], C[a + 2]) : 0.0f;   // sgn(0) = |0| = 0: an absent stencil adds nothing
+    Dy[a] = (kInterior || (ay >= 0 && ay + 2 < H)) ? dd(C[a], C[a + 1], C[a + 2]) : 0.0f;   // sgn(0) = |0| = 0: an absent stencil adds nothing
   }
   // cross terms anchored at rows y-1 .. y+3, columns x-1 (XL) and x (XR)
   float sL[kStrip + 1], sR[kStrip + 1], aR[kStrip + 1];
 #pragma unroll
   for (int a = 0; a < kStrip + 1; ++a) {
     const int ay = y + a - 1;
-    const bool rows = ay >= 0 && ay + 1 < H;
+    const bool rows = kInterior || (ay >= 0 && ay + 1 < H);
     float ab;
     sL[a] = sR[a] = aR[a] = 0.0f;
     if (rows && xm1) cross(L1[a], C[a + 1], L1[a + 1], C[a + 2], sL[a], ab);
@@ -127,7 +157,7 @@ __device__ __forceinline__ float smooth_strip(const RegLevel& lv, const float* _
   float lsum = 0.0f;
 #pragma unroll
   for (int j = 0; j < kStrip; ++j) {
-    if (y + j >= H) break;
+    if (!kInterior && y + j >= H) break;
     // dxx of row y+j anchored at x-2, x-1, x
     const float c = C[j + 2];
     const float dA = xm2 ? dd(L2[j], L1[j + 1], c) : 0.0f;
@@ -167,7 +197,10 @@ __global__ void __launch_bounds__(kThreads) smooth_loss_kernel(const __grid_cons
       const uint32_t b = fastdiv(item, lv.divSW), rem = item - b * lv.divSW.d_;
       const uint32_t sr = fastdiv(rem, lv.divW), x = rem - sr * lv.divW.d_;
       const size_t off = (size_t)b * lv.H * lv.W;
-      lsum += smooth_strip(lv, lv.x + off, lv.g ? lv.g + off : nullptr, (int)sr * kStrip, (int)x);
+      const int y0 = (int)sr * kStrip, x0 = (int)x;
+      float* const gb = lv.g ? lv.g + off : nullptr;
+      if (x0 >= 2 && x0 + 2 < lv.W && y0 >= 2 && y0 + kStrip + 1 < lv.H) lsum += smooth_strip<true>(lv, lv.x + off, gb, y0, x0);
+      else lsum += smooth_strip<false>(lv, lv.x + off, gb, y0, x0);
     }
   }
   local += (double)lsum * (double)p.lv[l].weight;
