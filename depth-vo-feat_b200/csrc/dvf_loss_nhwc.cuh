@@ -239,27 +239,43 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
     __syncwarp();
 
     // ---- phase B: channel work, pps pixels per step ------------------------------------------------
-    for (int s = 0; s < lpp; ++s) {
-      const int p = s * pps + grp;            // owner lane of the pixel my group handles in this step
-      const int pidx = base + p;
-      const bool plive = pidx < px_end;       // uniform over the group
-
-      // every load of the step goes out before any arithmetic: the target vector and the four taps of each view
-      const uint4 raw_t = ld_lane_vec<kBf16>(tgt_bb, (plive ? pidx : px_end - 1) * px_b + ch_b, half_b, plive ? 1u : 0u);
+    // every load of a step goes out before any arithmetic: the target vector and the four taps of each view
+    struct StepRegs {
+      uint4 raw_t;
       uint4 raw[kV][4];
       int o_b[kV];
       unsigned pkv[kV];
       float4 cw[kV];   // {offset, predicates, w, e}
+    };
+    auto issue_loads = [&](int s, StepRegs& R) {
+      const int p = s * pps + grp;
+      const int pidx = base + p;
+      const bool plive = pidx < px_end;
+      R.raw_t = ld_lane_vec<kBf16>(tgt_bb, (plive ? pidx : px_end - 1) * px_b + ch_b, half_b, plive ? 1u : 0u);
 #pragma unroll
       for (int v = 0; v < kV; ++v) {
-        cw[v] = *reinterpret_cast<const float4*>(&s_cell[warp][v][p][0]);
-        o_b[v] = __float_as_int(cw[v].x) * px_b + ch_b;
-        pkv[v] = __float_as_uint(cw[v].y);
-        raw[v][0] = ld_lane_vec<kBf16>(src_bb[v], o_b[v], half_b, pkv[v] & 1u);
-        raw[v][1] = ld_lane_vec<kBf16>(src_bb[v], o_b[v] + px_b, half_b, pkv[v] & 2u);
-        raw[v][2] = ld_lane_vec<kBf16>(src_bb[v], o_b[v] + row_b, half_b, pkv[v] & 4u);
-        raw[v][3] = ld_lane_vec<kBf16>(src_bb[v], o_b[v] + row_b + px_b, half_b, pkv[v] & 8u);
+        R.cw[v] = *reinterpret_cast<const float4*>(&s_cell[warp][v][p][0]);
+        R.o_b[v] = __float_as_int(R.cw[v].x) * px_b + ch_b;
+        R.pkv[v] = __float_as_uint(R.cw[v].y);
+        R.raw[v][0] = ld_lane_vec<kBf16>(src_bb[v], R.o_b[v], half_b, R.pkv[v] & 1u);
+        R.raw[v][1] = ld_lane_vec<kBf16>(src_bb[v], R.o_b[v] + px_b, half_b, R.pkv[v] & 2u);
+        R.raw[v][2] = ld_lane_vec<kBf16>(src_bb[v], R.o_b[v] + row_b, half_b, R.pkv[v] & 4u);
+        R.raw[v][3] = ld_lane_vec<kBf16>(src_bb[v], R.o_b[v] + row_b + px_b, half_b, R.pkv[v] & 8u);
       }
+    };
+    // (software-pipelining the loads of step s+1 under the arithmetic of step s needs ~170 registers = 3 CTAs per SM
+    // and came out slower: 262 vs 258 us fp32, 274 vs 247 us bf16)
+    for (int s = 0; s < lpp; ++s) {
+      const int p = s * pps + grp;            // owner lane of the pixel my group handles in this step
+      const int pidx = base + p;
+      const bool plive = pidx < px_end;       // uniform over the group
+      StepRegs R;
+      issue_loads(s, R);
+      const uint4 raw_t = R.raw_t;
+      uint4 (&raw)[kV][4] = R.raw;
+      int (&o_b)[kV] = R.o_b;
+      unsigned (&pkv)[kV] = R.pkv;
+      float4 (&cw)[kV] = R.cw;
       float tg[kVec], gt[kVec];
       VecIO<kBf16>::widen(raw_t, tg);
 #pragma unroll
