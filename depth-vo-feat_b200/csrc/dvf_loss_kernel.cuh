@@ -321,10 +321,15 @@ __device__ __forceinline__ int cta_of_unit(int g, int G, int T) {
   return (int)((((long long)g + 1) * G - 1) / T);
 }
 
-#ifndef DVF_C3_MINBLOCKS   // experiment builds: 5 CTAs per SM (96 registers, spills) 75.0 us, with folded sums 71.3 us, kept 67.6
-#define DVF_C3_MINBLOCKS 4
+// Resident CTAs per SM the register allocation is sized for.  One or two views: 4 (128 registers; 5 CTAs = 96 registers
+// spill: 75.0 us against 67.6 on C2; 3 CTAs = 168 registers: 74.2).  Three or four views keep too much state for 128
+// registers (132 / 332 bytes of spills): 3 CTAs per SM without spills are faster there (V = 4: 241.5 -> 220.8 us).
+#ifdef DVF_C3_MINBLOCKS   // experiment builds
+constexpr int c3_min_blocks(int) { return DVF_C3_MINBLOCKS; }
+#else
+constexpr int c3_min_blocks(int views) { return views >= 3 ? 3 : 4; }
 #endif
-template <int kV, bool kZeros, bool kExpl, bool kGrad, bool kTma, int kMinBlocks = DVF_C3_MINBLOCKS>
+template <int kV, bool kZeros, bool kExpl, bool kGrad, bool kTma, int kMinBlocks = c3_min_blocks(kV)>
 __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kernel(const __grid_constant__ LossParams prm) {
   constexpr int kC = 3;
   constexpr int kPlanes = 1 + kC + (kExpl ? kV : 0);   // streamed planes per chunk
