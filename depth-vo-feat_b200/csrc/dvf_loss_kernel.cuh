@@ -97,7 +97,7 @@ static __device__ __noinline__ ChainGrad chain_backward_exact(const float* P /*s
 }
 
 // out-of-line so that their register / stack needs (sinf/cosf slow paths, fp64) stay out of the pixel loop
-static __device__ __noinline__ float trig_of(float a, int want_sin) { return want_sin ? sinf(a) : cosf(a); }
+static __device__ __noinline__ float trig_of(float a, int want_sin) { return want_sin ? torch_sinf(a) : torch_cosf(a); }
 static __device__ __noinline__ void level_gM(const float* K, float ds, const float* gP /*12, smem*/, double* dst) {
   float Ks[9];
   scaled_K(K, ds, Ks);
@@ -131,7 +131,7 @@ __device__ __forceinline__ void load_matrices(const LossParams& prm, const Level
   const int tid = threadIdx.x;
   if (prm.pose_vec) {
     // Three short stages, each spread over threads so that the prologue costs one global-load latency plus a
-    // few hundred cycles: (1) fetch vec / K / K^-1, (2) sinf/cosf and the level's scaled intrinsics,
+    // few hundred cycles: (1) fetch vec / K / K^-1, (2) sin / cos (torch-CPU order, dvf_pose.cuh) and the level's scaled intrinsics,
     // (3) every thread of the first kV*12 composes R and takes one entry of P = K_s @ [R|t].
     // Operation order per entry is identical to dvf_pose_proj_fwd.
     __shared__ float s_vec[kV][6];

@@ -117,3 +117,24 @@ DVF_EXPORT int dvf_pose_proj_bwd(const float* gP, const float* gposemat, const f
       gP, gposemat, vec, K, B, V, rotation, sc, gvec);
   return launch_status();
 }
+
+// ---- torch-CPU's fp32 sin / cos as a stand-alone operator (dvf_pose.cuh: torch_sinf / torch_cosf) -------------------
+namespace dvf {
+__global__ void torch_trig_kernel(const float* __restrict__ x, long long n, float* __restrict__ s, float* __restrict__ c) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    if (s) s[i] = torch_sinf(v);
+    if (c) c[i] = torch_cosf(v);
+  }
+}
+}  // namespace dvf
+
+DVF_EXPORT int dvf_torch_sincos(const float* x, int64_t n, float* sin_out, float* cos_out, void* stream) {
+  if (n < 0) return DVF_EINVAL_SHAPE;
+  if (n == 0) return DVF_OK;
+  if (!x || (!sin_out && !cos_out)) return DVF_EINVAL_NULL;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 8ll * dvf::num_sms()) blocks = 8ll * dvf::num_sms();
+  dvf::torch_trig_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, sin_out, cos_out);
+  return dvf::launch_status();
+}

@@ -17,6 +17,44 @@ __device__ __forceinline__ void mm3(const float* a, const float* b, float* out) 
       out[r * N + c] = add(add(mul(a[r * 3 + 0], b[0 * N + c]), mul(a[r * 3 + 1], b[1 * N + c])), mul(a[r * 3 + 2], b[2 * N + c]));
 }
 
+// ---- torch-CPU's fp32 sin / cos, bit for bit -------------------------------------------------------------------------
+// inverse_warp.py:89-106 takes torch.cos / torch.sin of the Euler angles.  On the CPU torch evaluates them with MKL's
+// VML (vmsSin / vmsCos, high-accuracy mode), whose FMA code path is: n = round(|x| / pi) by the 1.5 * 2^23 trick in
+// fp32, r = |x| - n * pi in fp64 (pi in two parts), an odd degree-9 polynomial in fp64, ONE rounding to fp32, sign from
+// the parity of n.  fp64 FMAs are IEEE-exact on the GPU as well, so the same sequence gives the same bits; CUDA's sinf /
+// cosf agree with it on only ~93 % of inputs, and a projection matrix that is 1 ulp off moves bilinear cells and validity
+// masks.  Valid for |x| <= 10000 (above that MKL switches to a table-driven reduction and this falls back to sinf /
+// cosf).  Runs once per (image, view) in a kernel prologue: its cost is nil.  Pinned by tests/golden/trig_f32.npz.
+__device__ __forceinline__ float torch_trig_poly(double r) {
+  const double r2 = __dmul_rn(r, r);
+  double p = 0x1.5dbdf0e4c7deep-19;
+  p = __fma_rn(p, r2, -0x1.9f6ffeea73463p-13);
+  p = __fma_rn(p, r2, 0x1.110ed3804ca96p-7);
+  p = __fma_rn(p, r2, -0x1.55554bc836587p-3);
+  p = __dmul_rn(r2, p);
+  return __double2float_rn(__fma_rn(p, r, r));
+}
+__device__ __forceinline__ double torch_trig_reduce(float ax, float n) {
+  double r = (double)ax;
+  r = __fma_rn(-(double)n, 0x1.921fb5444p+1, r);            // pi, high 34 bits
+  return __fma_rn(-(double)n, 0x1.68c234c4c6629p-38, r);    // pi, rest
+}
+static __device__ __noinline__ float torch_sinf(float x) {
+  const float ax = fabsf(x);
+  if (!(ax <= 10000.0f)) return sinf(x);
+  const float y = __fmaf_rn(ax, 0x1.45f306p-2f, 12582912.0f);
+  const float n = __fsub_rn(y, 12582912.0f);
+  const uint32_t sign = (__float_as_uint(x) & 0x80000000u) ^ (__float_as_uint(y) << 31);
+  return __uint_as_float(__float_as_uint(torch_trig_poly(torch_trig_reduce(ax, n))) ^ sign);
+}
+static __device__ __noinline__ float torch_cosf(float x) {
+  const float ax = fabsf(x);
+  if (!(ax <= 10000.0f)) return cosf(x);
+  const float y = __fmaf_rn(__fadd_rn(ax, 0x1.921fb6p+0f), 0x1.45f306p-2f, 12582912.0f);
+  const float n = __fsub_rn(__fsub_rn(y, 12582912.0f), 0.5f);
+  return __uint_as_float(__float_as_uint(torch_trig_poly(torch_trig_reduce(ax, n))) ^ (__float_as_uint(y) << 31));
+}
+
 // euler2mat given the six trigonometric values (cz, sz, cy, sy, cx, sx): lets callers evaluate sinf/cosf in
 // parallel threads and compose afterwards; identical operation order to rotation_fwd
 __device__ __forceinline__ void euler_compose(float z, float cz, float sz, float cy, float sy, float cx, float sx, float* R) {
@@ -33,7 +71,7 @@ __device__ __forceinline__ void euler_compose(float z, float cz, float sz, float
 __device__ __forceinline__ void rotation_fwd(const float* ang, int rotation, float* R) {
   if (rotation == DVF_ROT_EULER) {
     const float x = ang[0], y = ang[1], z = ang[2];
-    euler_compose(z, cosf(z), sinf(z), cosf(y), sinf(y), cosf(x), sinf(x), R);
+    euler_compose(z, torch_cosf(z), torch_sinf(z), torch_cosf(y), torch_sinf(y), torch_cosf(x), torch_sinf(x), R);
   } else {
     float q[4] = {add(mul(ang[0], 0.0f), 1.0f), ang[0], ang[1], ang[2]};  // :125
     float ss = 0.0f;

@@ -235,6 +235,13 @@ int dvf_caffe_warp_bwd(const float* top_diff, const float* img, const float* coo
 int dvf_caffe_abs_loss(const float* a, const float* b, uint64_t count, int32_t num, float weight, float* loss, float* ga,
                        float* gb, void* workspace, void* stream);
 
+/* ---- torch.sin / torch.cos of fp32 values exactly as torch-CPU evaluates them ------------------
+ * (reference: inverse_warp.py:89-91,98-99,105-106 -- euler2mat's torch.cos / torch.sin, which on the
+ * CPU run MKL's VML in high-accuracy mode).  Bit-identical to torch 2.11 CPU for |x| <= 10000; larger
+ * arguments use CUDA's sinf / cosf.  The pose entries above use the same routine.  Either output may
+ * be NULL.                                                                                        */
+int dvf_torch_sincos(const float* x, int64_t n, float* sin_out, float* cos_out, void* stream);
+
 /* ---- diagnostics -----------------------------------------------------------
  * Compares the shared-reciprocal IEEE division of the coordinate chain with
  * __fdiv_rn on n pseudo-random operand pairs (mode 0: float divisors, mode 1:

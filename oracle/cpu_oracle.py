@@ -54,6 +54,14 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def torch_trig(x):
+    """torch.sin / torch.cos (CPU fp32) of x as restated in oracle/torch_trig.h -> (sin, cos)"""
+    x = _f32(x).reshape(-1)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib().dvfo_torch_trig(_p(x), C.c_long(x.size), _p(s), _p(c))
+    return s, c
+
+
 def pose_vec2mat(vec, rotation_mode="euler"):
     vec = _f32(vec)
     n = vec.shape[0]

@@ -26,12 +26,22 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "torch_trig.h"   /* torch-CPU's fp32 sin / cos (MKL VML, HA) restated */
+
 #define DVFO_API __attribute__((visibility("default")))
 
 enum { DVFO_PAD_ZEROS = 0, DVFO_PAD_BORDER = 1 };
 enum { DVFO_ROT_EULER = 0, DVFO_ROT_QUAT = 1 };
 
-DVFO_API int dvfo_version(void) { return 1; }
+DVFO_API int dvfo_version(void) { return 2; }
+
+/* torch.sin / torch.cos of n fp32 values (torch_trig.h) */
+DVFO_API void dvfo_torch_trig(const float *x, long n, float *s, float *c) {
+  for (long i = 0; i < n; ++i) {
+    s[i] = dvfo_torch_sinf(x[i]);
+    c[i] = dvfo_torch_cosf(x[i]);
+  }
+}
 
 /* ------------------------------------------------------------------------ */
 /* small dense helpers                                                       */
@@ -67,9 +77,10 @@ static inline float dot3_fma(float m0, float m1, float m2, float c0, float c1,
 /* euler2mat, inverse_warp.py:77-114:  R = (Rx @ Ry) @ Rz. */
 static void euler2mat_one(const float *ang, float *R) {
   float x = ang[0], y = ang[1], z = ang[2];
-  float cz = cosf(z), sz = sinf(z);
-  float cy = cosf(y), sy = sinf(y);
-  float cx = cosf(x), sx = sinf(x);
+  /* torch.cos / torch.sin, :89-90, :98-99, :105-106 -- see torch_trig.h */
+  float cz = dvfo_torch_cosf(z), sz = dvfo_torch_sinf(z);
+  float cy = dvfo_torch_cosf(y), sy = dvfo_torch_sinf(y);
+  float cx = dvfo_torch_cosf(x), sx = dvfo_torch_sinf(x);
   float zero = z * 0.0f;       /* :93 zeros = z.detach()*0  */
   float one = zero + 1.0f;     /* :94                         */
   float zm[9] = {cz, -sz, zero, sz, cz, zero, zero, zero, one};

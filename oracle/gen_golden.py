@@ -176,6 +176,59 @@ def case_regularisers(mods, name, B, H, W, n_scales, seed):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
+def case_trig(name, n, seed):
+    """torch.sin / torch.cos (CPU fp32) -- what euler2mat (inverse_warp.py:89-106) evaluates -- on n angles: PoseExpNet-scale
+    (0.01 N(0,1)), KITTI-like (0.005 N(0,1)), unit-scale, uniform over +-pi, +-100, +-10000 and special values."""
+    g = torch.Generator().manual_seed(seed)
+    k = n // 8
+    parts = [torch.randn(2 * k, generator=g) * 0.01, torch.randn(2 * k, generator=g) * 0.005, torch.randn(k, generator=g),
+             (torch.rand(k, generator=g) * 2 - 1) * float(np.pi), (torch.rand(k, generator=g) * 2 - 1) * 100.0,
+             (torch.rand(k, generator=g) * 2 - 1) * 10000.0]
+    special = torch.tensor([0.0, -0.0, float(np.pi), -float(np.pi), float(np.pi) / 2, -float(np.pi) / 2, 1e-30, -1e-40, 1e-45,
+                            10000.0, -10000.0, 0.53233, 1.0, -1.0, 3.0, 6.2831855, 1.5707964, 0.7853982], dtype=torch.float32)
+    x = torch.cat(parts + [special]).to(torch.float32)
+    xs = torch.stack([x, x], 1)[:, 0]          # the reference takes sin / cos of strided views (angle[:, k])
+    s, c = torch.sin(xs), torch.cos(xs)
+    assert torch.equal(s, torch.sin(x)) and torch.equal(c, torch.cos(x))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kind="trig", x=_np(x), sin=_np(s), cos=_np(c))
+
+
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def case_config1(mods, name, B, H, W, seed, stride=97):
+    """BASELINE configs[0]: inverse_warp + photometric_reconstruction_loss (loss_functions.py:7-20) on a B x 3 x 128 x 416
+    stereo + temporal batch.  Inputs are regenerated from the seed by dvf_b200.synthetic (their SHA-256 is stored so that a
+    generator drift is detected); outputs that must match bit for bit are stored as SHA-256 plus packed mask bits, gradients
+    as strided samples (every `stride`-th element) plus their fp64 sums."""
+    d = syn.stereo_temporal_batch(B, H, W, seed=seed)
+    t = {k: v.clone() for k, v in d.items()}
+    for k in ("depth", "T_2to1", "T_R2L"):
+        t[k].requires_grad_(True)
+    _reset(mods)
+    iw = mods["inverse_warp"]
+    out = dict(kind="config1", B=B, H=H, W=W, seed=seed, stride=stride,
+               inputs_sha=np.array([_sha(_np(d[k])) for k in sorted(d)]), input_names=np.array(sorted(d)))
+    for tag, src, pose in (("R1", "img_R1", "T_2to1"), ("L2", "img_L2", "T_R2L")):
+        w = iw.inverse_warp(d[src], d["depth"], d[pose], d["intrinsics"], d["intrinsics_inv"])
+        valid = (1 - (w == 0).prod(1)).to(torch.uint8)
+        out["warped_sha_" + tag] = _sha(_np(w))
+        out["warped_sample_" + tag] = _np(w).reshape(-1)[::stride].copy()
+        out["valid_bits_" + tag] = np.packbits(_np(valid).reshape(-1))
+        out["P_" + tag] = _np(d["intrinsics"] @ iw.pose_vec2mat(d[pose]))
+    _reset(mods)
+    loss = mods["loss_functions"].photometric_reconstruction_loss(t["img_R2"], t["img_R1"], t["img_L2"], t["depth"], t["T_2to1"],
+                                                                  t["T_R2L"], t["intrinsics"], t["intrinsics_inv"])
+    loss.backward()
+    gd = _np(t["depth"].grad)
+    out.update(loss=_np(loss), g_T_2to1=_np(t["T_2to1"].grad), g_T_R2L=_np(t["T_R2L"].grad), g_depth_sha=_sha(gd),
+               g_depth_sample=gd.reshape(-1)[::stride].copy(), g_depth_sum=np.float64(gd.astype(np.float64).sum()),
+               g_depth_abs_sum=np.float64(np.abs(gd.astype(np.float64)).sum()), g_depth_max=np.float32(np.abs(gd).max()))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
 def main():
     warnings.filterwarnings("ignore")
     torch.set_num_threads(1)
@@ -194,6 +247,8 @@ def main():
     case_sfm(mods, "sfm_old_2scales_mask", 2, 32, 104, 2, seed=11, with_mask=True, rot="euler", pad="zeros", old=True)
     case_se3("se3_exp", 6, seed=12)
     case_regularisers(mods, "regularisers", 2, 30, 52, 3, seed=13)
+    case_trig("trig_f32", 1 << 17, seed=14)
+    case_config1(mods, "config1_4x3x128x416", 4, 128, 416, seed=15)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("wrote", sorted(os.listdir(OUT)), f"{tot / 1024:.0f} KiB")
 

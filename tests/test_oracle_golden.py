@@ -11,10 +11,10 @@ from helpers import assert_close, golden, golden_names, rel_err, ulp_diff
 def test_inverse_warp_golden(oracle, name):
     g = golden(name)
     rot, pad = g["rotation_mode"], g["padding_mode"]
-    # pose -> P: sin/cos of glibc vs torch's SLEEF may differ in the last place
+    # pose -> P: torch-CPU's sin / cos are restated bit for bit (oracle/torch_trig.h)
     pm = oracle.pose_vec2mat(g["pose"], rot)
-    assert ulp_diff(pm, g["posemat"]) <= 2
-    P = oracle.project(g["K"], g["posemat"])
+    assert np.array_equal(pm, g["posemat"]), "pose_vec2mat must be bit-identical to the reference"
+    P = oracle.project(g["K"], pm)
     assert np.array_equal(P, g["P"]), "K @ pose_mat must reproduce torch's tiny-bmm rounding"
     # per-pixel path on the reference's own P: bit-exact
     warped, valid = oracle.inverse_warp_P(g["img"], g["depth"], g["P"], g["Kinv"], pad)
@@ -72,6 +72,45 @@ def test_sfm_golden(oracle, name):
             gpose[:, v] += oracle.pose_bwd(r["gP"][:, v], Ks, g["pose"][:, v], rot)
     assert abs(total - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
     assert_close(gpose, g["g_pose"], what="gpose")
+
+
+def test_trig_golden(oracle):
+    """oracle/torch_trig.h == torch.sin / torch.cos of the reference's euler2mat (inverse_warp.py:89-106), bit for bit"""
+    g = golden("trig_f32")
+    s, c = oracle.torch_trig(g["x"])
+    assert np.array_equal(s.view(np.uint32), g["sin"].view(np.uint32))
+    assert np.array_equal(c.view(np.uint32), g["cos"].view(np.uint32))
+    import torch
+    x = (torch.randn(1 << 18, generator=torch.Generator().manual_seed(3)) * 2.0).numpy()   # and live, on this CPU
+    s, c = oracle.torch_trig(x)
+    assert np.array_equal(s, torch.sin(torch.from_numpy(x)).numpy()) and np.array_equal(c, torch.cos(torch.from_numpy(x)).numpy())
+
+
+def test_config1_golden(oracle):
+    """BASELINE configs[0] (4 x 3 x 128 x 416): oracle vs the reference run at full size -- P, warped images and masks bit
+    for bit (SHA-256 / packed bits), loss and gradients at 1e-5."""
+    import hashlib
+    from dvf_b200 import synthetic as syn
+    g = golden("config1_4x3x128x416")
+    B, H, W = int(g["B"]), int(g["H"]), int(g["W"])
+    d = {k: v.numpy() for k, v in syn.stereo_temporal_batch(B, H, W, seed=int(g["seed"])).items()}
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()   # noqa: E731
+    assert [sha(d[k]) for k in sorted(d)] == list(g["inputs_sha"]), "synthetic generator drifted: regenerate the goldens"
+    Ps = []
+    for tag, src, pose in (("R1", "img_R1", "T_2to1"), ("L2", "img_L2", "T_R2L")):
+        P = oracle.project(d["intrinsics"], oracle.pose_vec2mat(d[pose]))
+        assert np.array_equal(P, g["P_" + tag])
+        w, v = oracle.inverse_warp_P(d[src], d["depth"], P, d["intrinsics_inv"], "zeros")
+        assert sha(w) == g["warped_sha_" + tag], "warped image differs from the reference"
+        assert np.array_equal(np.packbits(v.reshape(-1)), g["valid_bits_" + tag])
+        Ps.append(P)
+    r = oracle.photo_loss_P(d["img_R2"], [d["img_R1"], d["img_L2"]], d["depth"], np.stack(Ps, 1), d["intrinsics_inv"])
+    assert abs(r["terms"].sum() - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    st = int(g["stride"])
+    assert_close(r["gdepth"].reshape(-1)[::st], g["g_depth_sample"], what="gdepth sample")
+    assert abs(np.abs(r["gdepth"].astype(np.float64)).sum() - float(g["g_depth_abs_sum"])) <= 1e-6 * float(g["g_depth_abs_sum"])
+    assert_close(oracle.pose_bwd(r["gP"][:, 0], d["intrinsics"], d["T_2to1"]), g["g_T_2to1"], what="g_T_2to1")
+    assert_close(oracle.pose_bwd(r["gP"][:, 1], d["intrinsics"], d["T_R2L"]), g["g_T_R2L"], what="g_T_R2L")
 
 
 def test_smooth_and_explainability_match_closed_form(oracle):
