@@ -70,8 +70,12 @@ def test_trig_golden_bit_exact(ops, oracle):
 
 
 def test_trig_matches_live_torch_cpu():
-    """the same against torch.sin / torch.cos evaluated on this machine's CPU: 2^24 angles of every magnitude class
-    (torch is present on the GPU box; the reference checkout is not needed)."""
+    """the same against torch.sin / torch.cos evaluated on THIS machine's CPU: 2^24 angles of every magnitude class.
+    torch-CPU's fp32 sin / cos are MKL VML kernels that MKL picks by CPU model (oracle/torch_trig.h): the FMA kernels
+    (AVX2 / AVX-512 on Intel parts, what generated tests/golden/trig_f32.npz) are the pinned target and must match bit
+    for bit; MKL's other code paths (pre-FMA SSE / AVX, non-Intel hosts) round ~2e-5 of the angles differently, i.e.
+    torch-CPU does not agree with itself across hosts there.  So: bit-exact when this host runs the pinned kernels,
+    else every value within 1 ulp and fewer than 1e-4 of them different (the count is printed either way)."""
     gen = torch.Generator().manual_seed(77)
     n = 1 << 21
     x = torch.cat([torch.randn(n, generator=gen) * sc for sc in (1e-3, 0.01, 0.1, 1.0, 10.0)] +
@@ -81,8 +85,20 @@ def test_trig_matches_live_torch_cpu():
     near = torch.cat([torch.nextafter(k.float(), torch.tensor(float(sgn) * 1e9)) for sgn in (-1, 1)] + [k.float()])
     x = torch.cat([x, near]).contiguous()
     s, c = _gpu_sincos(x.numpy())
-    assert np.array_equal(s.view(np.uint32), torch.sin(x).numpy().view(np.uint32))
-    assert np.array_equal(c.view(np.uint32), torch.cos(x).numpy().view(np.uint32))
+    g = golden("trig_f32")
+    gx = torch.from_numpy(g["x"])
+    host_is_pinned = (np.array_equal(torch.sin(gx).numpy().view(np.uint32), g["sin"].view(np.uint32)) and
+                      np.array_equal(torch.cos(gx).numpy().view(np.uint32), g["cos"].view(np.uint32)))
+    for name, mine, ref in (("sin", s, torch.sin(x).numpy()), ("cos", c, torch.cos(x).numpy())):
+        diff = mine.view(np.uint32) != ref.view(np.uint32)
+        nd = int(diff.sum())
+        print(f"live torch-CPU {name}: {nd} of {x.numel()} differ; host runs the pinned MKL kernels: {host_is_pinned}; "
+              f"cpu capability {torch.backends.cpu.get_cpu_capability()}")
+        if host_is_pinned:
+            assert nd == 0, f"{name}: {nd} values differ from torch-CPU on a host that reproduces the golden vectors"
+        else:
+            ulp = np.abs(mine.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+            assert nd < 1e-4 * x.numel() and int(ulp.max()) <= 1, (name, nd, int(ulp.max()))
 
 
 @pytest.mark.parametrize("rot", ["euler", "quat"])
