@@ -2,22 +2,33 @@
 """Benchmark of the fused inverse-warp + reconstruction-loss hot path (BASELINE.json metric:
 warped px/s of the fused warp+loss fwd+bwd, and % of the HBM roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
-    python bench.py --impl reference [--steps K] [--warmup W]            # the reference's CPU PyTorch path (port)
+    python bench.py [--config C2] [--gpus N] [--steps K] [--warmup W]     # this repo's CUDA path
+    python bench.py --impl reference [--config C2] [--steps K] [--warmup W]  # the reference's CPU PyTorch path (port)
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], SURVEY 8d "C2"): 4-scale stereo photometric loss fwd+bwd, batch 64
-per GPU at 128x416 (levels 128x416, 64x208, 32x104, 16x52), one source view (the rectified-stereo pose),
-fp32 NCHW, synthetic KITTI-shaped inputs, image pyramids prebuilt (they are inputs of the path, 8d).
-A step = ONE launch of dvf_photo_loss_fused_pose (pose_vec2mat + projection in the kernel prologue, warp + loss +
-all gradients over all levels, pose backward in the epilogue).  Steps rotate over several distinct input sets whose total
-size exceeds L2; one CUDA graph holds one round of them (--single-step-graphs: one graph per step).
-Multi-GPU: batch sharded, B=64 per rank (weak scaling), no data-path collective; one NCCL all-reduce of the
-loss terms closes the timed region (logging exchange).
+Workloads (BASELINE.json configs):
+    C1      configs[0]: loss_functions.photometric_reconstruction_loss (2 views, 1 scale) on 4 x 3 x 128 x 416
+    C2      configs[1]: 4-scale stereo photometric loss fwd+bwd, batch 64 per GPU at 128 x 416, 1 view  [default]
+    C3      configs[2]: stereo + temporal depth-odometry loss: 2 views (temporal pose at PoseExpNet scale + stereo),
+            explainability masks, 4 scales, GLOBAL batch 256 sharded over the GPUs (strong scaling)
+    C4      configs[3]: photometric loss (2 views, 128 x 416) + feature reconstruction loss on 64-channel maps at 1/4
+            resolution (bf16 channels-last, gradients to all three maps), GLOBAL batch 128
+    C5loss  configs[4], the warp+loss part: 256 x 832, 4 scales, 2 views + masks, batch 64 per GPU (512 on 8)
+A step = the fused launch(es) of one loss evaluation with all gradients (pose_vec2mat + projection in the kernel
+prologue, warp + loss + gradients over all levels and views, pose backward in the epilogue).  Image pyramids are
+prebuilt inputs.  Steps rotate over several distinct input sets whose total size exceeds L2; CUDA graphs
+hold --graph-steps consecutive steps.
+Multi-GPU: batch sharded, no data-path collective.  The loss terms are all-reduced EVERY step (NCCL, <= 16 floats) on a
+side stream inside the captured graph, so the exchange of step i overlaps the kernel of step i+1 as it would in a
+training loop that logs its loss.  The main value keeps the workload of --config at every N (C2: fixed batch per GPU =
+weak scaling, so that the driver's per-N efficiency compares like with like); when --config is C2 the line also carries
+`strong_c3`: the C3 workload at a FIXED global batch of 256 on the same N GPUs.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
+import glob
 import json
 import os
 import subprocess
@@ -35,7 +46,23 @@ import torch  # noqa: E402
 
 METRIC = "warped_px_per_s_fused_warp_loss_fwd_bwd"
 UNIT = "warped px/s"
-H, W, LEVELS = 128, 416, 4
+
+WORKLOADS = {
+    "C1": dict(H=128, W=416, levels=1, views=2, expl=False, batch=4, batch_is="per_gpu", temporal="kitti",
+               title="C1: loss_functions.photometric_reconstruction_loss fwd+bwd, 2 views, 4x3x128x416 (BASELINE configs[0])"),
+    "C2": dict(H=128, W=416, levels=4, views=1, expl=False, batch=64, batch_is="per_gpu", temporal=None,
+               title="C2: 4-scale stereo photometric loss fwd+bwd, batch 64/GPU at 128x416 (BASELINE configs[1])"),
+    "C3": dict(H=128, W=416, levels=4, views=2, expl=True, batch=256, batch_is="global", temporal="tiny",
+               title="C3: stereo+temporal depth-odometry loss fwd+bwd, 2 views + explainability masks, 4 scales, "
+                     "global batch 256 at 128x416 (BASELINE configs[2])"),
+    "C4": dict(H=128, W=416, levels=1, views=2, expl=False, batch=128, batch_is="global", temporal="kitti",
+               feature=dict(C=64, h=32, w=104, dtype="bf16"),
+               title="C4: photometric loss (2 views, 128x416) + feature reconstruction loss on 64-ch bf16 channels-last maps "
+                     "at 32x104 with gradients to all maps, global batch 128 (BASELINE configs[3])"),
+    "C5loss": dict(H=256, W=832, levels=4, views=2, expl=True, batch=64, batch_is="per_gpu", temporal="kitti",
+                   title="C5loss: warp+loss part of the high-res step, 256x832, 4 scales, 2 views + masks, batch 64/GPU "
+                         "(BASELINE configs[4]; the conv nets stay on cuDNN and are not part of the path)"),
+}
 
 
 def parse():
@@ -44,16 +71,20 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="batch per GPU")
+    ap.add_argument("--config", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's batch (per GPU or global, as the workload defines it)")
     ap.add_argument("--sets", type=int, default=4, help="distinct input sets rotated through (working set > L2)")
+    ap.add_argument("--graph-steps", type=int, default=16, help="consecutive steps per CUDA graph")
     ap.add_argument("--prewarm-ms", type=float, default=400.0, help="untimed clock ramp before the W warm-up steps")
     ap.add_argument("--roofline-ms", type=float, default=1500.0, help="length of the dominant-kernel timing loop")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
-    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
-    ap.add_argument("--single-step-graphs", action="store_true", help="one CUDA graph per step instead of one per round of --sets steps")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="batch of the CPU legs (0 = the GPU arm's per-GPU batch)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip strong_c3 / unfused_gpu")
+    ap.add_argument("--no-pdl", action="store_true", help="plain launches instead of programmatic dependent launches (A/B)")
+    ap.add_argument("--no-allreduce", action="store_true", help="N > 1: no per-step exchange of the loss terms (A/B)")
     ap.add_argument("--iid-depth", action="store_true", help="stress case: iid-noise depth instead of the smooth field")
     return ap.parse_args()
 
@@ -61,18 +92,53 @@ def parse():
 # ------------------------------------------------------------------------------------------------
 # synthetic workload
 # ------------------------------------------------------------------------------------------------
-def make_inputs(B, seed, smooth=True):
-    """CPU tensors of one C2 batch: full-resolution target/source images, depth per level, stereo pose, K."""
+def local_batch(wl, world, override=0):
+    b = override or wl["batch"]
+    if wl["batch_is"] == "global":
+        if b % world:
+            raise SystemExit(f"global batch {b} does not divide over {world} GPUs")
+        return b // world, b
+    return b, b * world
+
+
+def make_inputs(wl, B, seed, smooth=True):
+    """CPU tensors of one batch: full-resolution target / source images, depth per level, poses [B,V,6], K
+    (+ explainability masks per level, + feature maps and their depth for C4)."""
     from dvf_b200 import synthetic as syn
-    tgt, src = syn.images(B, 3, H, W, seed + 1, smooth=True, n=2)
-    depths = [syn.depth(B, H >> s, W >> s, seed + 10 + s, smooth=smooth) for s in range(LEVELS)]
-    pose = syn.pose(B, "stereo", seed).unsqueeze(1)          # [B,1,6]
+    H, W, L, V = wl["H"], wl["W"], wl["levels"], wl["views"]
+    imgs = syn.images(B, 3, H, W, seed + 1, smooth=True, n=1 + V)
+    depths = [syn.depth(B, H >> s, W >> s, seed + 10 + s, smooth=smooth) for s in range(L)]
+    poses = [syn.pose(B, wl["temporal"], seed + 3)] if V == 2 else []
+    poses.append(syn.pose(B, "stereo", seed + 4))
     K, Kinv = syn.intrinsics(B, H, W)
-    return dict(tgt=tgt, src=src, depths=depths, pose=pose, K=K, Kinv=Kinv)
+    d = dict(tgt=imgs[0], srcs=imgs[1:], depths=depths, pose=torch.stack(poses, 1).contiguous(), K=K, Kinv=Kinv)
+    if wl["expl"]:
+        d["expl"] = [syn.explainability(B, V, H >> s, W >> s, seed + 20 + s) for s in range(L)]
+    f = wl.get("feature")
+    if f:
+        d["feat"] = syn.features(B, f["C"], f["h"], f["w"], seed + 30, n=1 + V)
+        d["feat_depth"] = syn.depth(B, f["h"], f["w"], seed + 40, smooth=smooth)
+        d["feat_K"], d["feat_Kinv"] = syn.intrinsics(B, f["h"], f["w"])
+    return d
 
 
-def warped_px(B, V=1):
-    return B * V * sum((H >> s) * (W >> s) for s in range(LEVELS))
+def warped_px(wl, B):
+    n = B * wl["views"] * sum((wl["H"] >> s) * (wl["W"] >> s) for s in range(wl["levels"]))
+    f = wl.get("feature")
+    if f:
+        n += B * wl["views"] * f["h"] * f["w"]
+    return n
+
+
+def config_dict(name, wl, world, args):
+    """The `config` object of the JSON line -- identical for the b200 and the reference arm."""
+    Bl, Bg = local_batch(wl, world, args.batch)
+    return {"workload": wl["title"], "name": name, "batch_per_gpu": Bl, "global_batch": Bg, "H": wl["H"], "W": wl["W"],
+            "levels": wl["levels"], "views": wl["views"], "explainability_masks": wl["expl"],
+            "feature_maps": wl.get("feature"), "layout": "NCHW fp32 images" + (", NHWC bf16 feature maps" if wl.get("feature") else ""),
+            "depth_field": "iid-noise (stress)" if args.iid_depth else "smooth (17x17 box-filtered disparity)",
+            "pyramid": "prebuilt inputs (SURVEY 8d)", "parallelism": f"batch-sharded dp{world}",
+            "scaling": "strong" if wl["batch_is"] == "global" else "weak"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -127,27 +193,46 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference / cpu baseline (oracle/torch_port.py restates the reference's torch op sequence)
+# the reference's torch operator sequence (oracle/torch_port.py restates it; used on the CPU as the reference arm /
+# cpu_baseline and on the GPU as the "unfused stock PyTorch" comparison)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_fn(B):
+def torch_port_step_fn(wl, B, device="cpu"):
     from oracle import torch_port as ref
-    d = make_inputs(B, seed=4242)
-    tgt, src, K, Kinv = d["tgt"], d["src"], d["K"], d["Kinv"]
+    d = make_inputs(wl, B, seed=4242)
+    mv = lambda t: t.to(device)   # noqa: E731
+    tgt, srcs, K, Kinv = mv(d["tgt"]), [mv(s) for s in d["srcs"]], mv(d["K"]), mv(d["Kinv"])
+    depths0 = [mv(x) for x in d["depths"]]
+    pose0 = mv(d["pose"])
+    expl0 = [mv(x) for x in d["expl"]] if wl["expl"] else None
+    f = wl.get("feature")
+    if f:
+        feat0 = [mv(x) for x in d["feat"]]
+        fdepth0, fK, fKi = mv(d["feat_depth"]), mv(d["feat_K"]), mv(d["feat_Kinv"])
+    L, V = wl["levels"], wl["views"]
 
     def step():
-        depths = [x.unsqueeze(1).clone().requires_grad_(True) for x in d["depths"]]
-        pose = d["pose"].clone().requires_grad_(True)
-        loss = ref.loss_multi_scale(tgt, [src], K, Kinv, depths, [None] * LEVELS, pose)
+        pose = pose0.clone().requires_grad_(True)
+        if L == 1 and V == 2:   # loss_functions.py:7-20
+            depth = depths0[0].clone().requires_grad_(True)
+            loss = ref.loss_two_view(tgt, srcs[0], srcs[1], depth, pose[:, 0], pose[:, 1], K, Kinv)
+            if f:               # unsupervise.py:104-111
+                feats = [x.clone().requires_grad_(True) for x in feat0]
+                fdepth = fdepth0.clone().requires_grad_(True)
+                loss = loss + ref.loss_two_view(feats[0], feats[1], feats[2], fdepth, pose[:, 0], pose[:, 1], fK, fKi)
+        else:                   # loss_functions_sfm.py:9-46
+            depths = [x.unsqueeze(1).clone().requires_grad_(True) for x in depths0]
+            masks = [x.clone().requires_grad_(True) for x in expl0] if expl0 else [None] * L
+            loss = ref.loss_multi_scale(tgt, srcs, K, Kinv, depths, masks, pose)
         loss.backward()
-        return float(loss.detach())
+        return loss.detach()
 
     return step
 
 
-def cpu_baseline(seconds, B):
+def cpu_baseline(wl, seconds, B):
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    step = cpu_reference_step_fn(B)
+    step = torch_port_step_fn(wl, B)
     step(); step()
     n, t0 = 0, time.perf_counter()
     while True:
@@ -156,35 +241,38 @@ def cpu_baseline(seconds, B):
         el = time.perf_counter() - t0
         if el >= seconds or n >= 200:
             break
-    return {"value": warped_px(B) * n / el, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} fwd+bwd iterations of the same 4-scale stereo loss at batch {B} ({warped_px(B)} warped px each), "
+    return {"value": warped_px(wl, B) * n / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} fwd+bwd iterations of the same workload at batch {B} ({warped_px(wl, B)} warped px each), "
                       f"torch {torch.__version__} CPU, {cores} threads, oracle/torch_port.py"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    wl = WORKLOADS[args.config]
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    B = args.cpu_batch
-    step = cpu_reference_step_fn(B)
+    Bl, _ = local_batch(wl, world, args.batch)
+    B = args.cpu_batch or Bl
+    step = torch_port_step_fn(wl, B)
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        float(step())
     el = time.perf_counter() - t0
-    val = warped_px(B) * args.steps / el
-    sample = (f"each step = fwd+bwd of the 4-scale stereo loss on a bounded batch of {B} (not {args.batch}); "
+    val = warped_px(wl, B) * args.steps / el
+    sample = (f"each step = fwd+bwd of the workload on one rank's batch of {B} on the host cores; "
               f"torch {torch.__version__} CPU, {cores} threads; reference op sequence restated in oracle/torch_port.py "
               f"(the reference checkout is not present on the GPU box)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if wl["batch_is"] == "global" else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "4-scale stereo photometric loss fwd+bwd, 128x416, CPU bounded sample", "batch": B,
-                   "levels": LEVELS, "views": 1},
+        "config": config_dict(args.config, wl, world, args),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -194,10 +282,344 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # this repo's CUDA path
 # ------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch.distributed as dist
+class Step:
+    """The fused launch(es) of one loss evaluation on one resident input set."""
+
+    def __init__(self, plans):
+        self.plans = plans
+        self.warped_px = sum(p.warped_px for p in plans)
+        self.bytes = sum(p.algorithmic_bytes() for p in plans)
+        self.n_launches = sum(p.n_launches for p in plans)
+        self.dominant = max(plans, key=lambda p: p.algorithmic_bytes())
+        self.n_terms = sum(p.terms.numel() for p in plans)
+
+    def copy_terms_into(self, buf):
+        o = 0
+        for p in self.plans:
+            buf[o:o + p.terms.numel()].copy_(p.terms)
+            o += p.terms.numel()
+
+    def launch(self):
+        for p in self.plans:
+            p.launch()
+
+
+def build_steps(wl, B, Bg, host, dev, sets, pdl):
     from dvf_b200 import ops
     from dvf_b200.plan import FusedLossPlan
+    H, W, L, V = wl["H"], wl["W"], wl["levels"], wl["views"]
+    sizes = [(H >> s, W >> s) for s in range(L)]
+    ds = [float(1 << s) for s in range(L)]
+    steps = []
+    for k in range(sets):
+        roll = lambda t: torch.roll(t, shifts=k, dims=0).contiguous().to(dev)   # noqa: E731
+        tgt_pyr = ops.area_pyramid(roll(host["tgt"]), sizes)
+        src_pyrs = [ops.area_pyramid(roll(s), sizes) for s in host["srcs"]]
+        pose, K, Kinv = roll(host["pose"]), roll(host["K"]), roll(host["Kinv"])
+        expl = [roll(x) for x in host["expl"]] if wl["expl"] else None
+        plans = [FusedLossPlan(tgt_pyr, [[sp[l] for sp in src_pyrs] for l in range(L)], [roll(x) for x in host["depths"]],
+                               pose, K, Kinv, expl_levels=expl, downscales=ds, global_batch=Bg, pdl=pdl)]
+        f = wl.get("feature")
+        if f:
+            cl = lambda t: roll(t).to(torch.bfloat16 if f["dtype"] == "bf16" else torch.float32).contiguous(   # noqa: E731
+                memory_format=torch.channels_last)
+            feats = [cl(x) for x in host["feat"]]
+            plans.append(FusedLossPlan([feats[0]], [feats[1:]], [roll(host["feat_depth"])], pose, roll(host["feat_K"]),
+                                       roll(host["feat_Kinv"]), map_grads=True, global_batch=Bg, pdl=pdl))
+        steps.append(Step(plans))
+    return steps
+
+
+class Runner:
+    """CUDA graphs over the rotating input sets; N > 1: the loss terms of every step are all-reduced on a side stream
+    inside the graph (step i's exchange overlaps step i+1's kernel; the graph joins the side stream at its end)."""
+
+    def __init__(self, steps, graph_steps, world, allreduce, only=None):
+        import torch.distributed as dist
+        self.steps, self.world = steps, world
+        self.n_sets = len(steps)
+        self.graph_steps = max(self.n_sets, (graph_steps // self.n_sets) * self.n_sets)
+        self.exchange = "none"
+        launch = (lambda s: s.launch()) if only is None else (lambda s: only(s).launch())
+        main = torch.cuda.Stream()
+        main.wait_stream(torch.cuda.current_stream())
+        xs = torch.cuda.Stream()
+        do_ar = world > 1 and allreduce
+        # term buffers of the exchange: one per step of the long graph (an all-reduce may still be in flight when the
+        # same input set is launched again)
+        self.xbuf = ([torch.zeros(steps[0].n_terms, device=steps[0].plans[0].terms.device) for _ in range(self.graph_steps)]
+                     if do_ar else None)
+
+        copied = {}
+
+        def body(i, captured):
+            st = steps[i % self.n_sets]
+            cur = torch.cuda.current_stream()
+            if do_ar and (i - self.n_sets) in copied:
+                cur.wait_event(copied.pop(i - self.n_sets))   # this input set's terms have left for the exchange
+            launch(st)
+            if do_ar:
+                # copy + all-reduce on the side stream: the loss kernels stay back to back on the main stream
+                xs.wait_stream(cur)
+                with torch.cuda.stream(xs):
+                    st.copy_terms_into(self.xbuf[i % self.graph_steps])
+                    ev = torch.cuda.Event()
+                    ev.record(xs)
+                    copied[i] = ev
+                    dist.all_reduce(self.xbuf[i % self.graph_steps])
+        with torch.cuda.stream(main):
+            for i in range(self.n_sets):         # untimed: first launches, NCCL communicator warm-up
+                body(i, False)
+            main.wait_stream(xs)
+            torch.cuda.synchronize()
+            copied.clear()
+            self.single = []
+            try:
+                self.long = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.long, stream=main, capture_error_mode="thread_local"):
+                    for i in range(self.graph_steps):
+                        body(i, True)
+                    if do_ar:
+                        torch.cuda.current_stream().wait_stream(xs)
+                copied.clear()
+                for k in range(self.n_sets):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=main, capture_error_mode="thread_local"):
+                        body(k, True)
+                        if do_ar:
+                            torch.cuda.current_stream().wait_stream(xs)
+                    copied.clear()
+                    self.single.append(g)
+                self.exchange = ("NCCL all-reduce of the loss terms every step, on a side stream inside the CUDA graph"
+                                 if do_ar else "none")
+            except Exception as e:   # NCCL refused capture: eager per-step exchange, still every step
+                if not do_ar:
+                    raise
+                torch.cuda.synchronize()
+                copied.clear()
+                self.long, self.single = None, []
+                self.exchange = f"NCCL all-reduce every step, eager on a side stream (graph capture failed: {type(e).__name__})"
+                self._eager = body
+        torch.cuda.current_stream().wait_stream(main)
+        torch.cuda.synchronize()
+
+    def run(self, n):
+        if self.long is None:
+            for i in range(n):
+                self._eager(i, False)
+            return
+        q, r = divmod(n, self.graph_steps)
+        for _ in range(q):
+            self.long.replay()
+        for i in range(r):
+            self.single[i % self.n_sets].replay()
+
+    def spin(self, ms):
+        t_end = time.perf_counter() + ms / 1e3
+        while time.perf_counter() < t_end:
+            self.run(2 * self.graph_steps)
+            torch.cuda.synchronize()
+
+
+def timed(runner, n, world, dev):
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    runner.run(n)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def csrc_sha16():
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(PKG, "csrc", "*"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measure_workload(name, wl, args, world, rank, dev, sampler, steps_n, warmup_n, roofline=True):
+    """value (K steps, device-timed, max over ranks) and, on request, the dominant kernel's roofline."""
+    Bl, Bg = local_batch(wl, world, args.batch if name == args.config else 0)
+    host = make_inputs(wl, Bl, seed=1000 + rank, smooth=not args.iid_depth)
+    steps = build_steps(wl, Bl, Bg, host, dev, args.sets, pdl=(args.sets >= 2 and not args.no_pdl))
+    runner = Runner(steps, args.graph_steps, world, not args.no_allreduce)
+    wpx = steps[0].warped_px
+    assert wpx == warped_px(wl, Bl)
+    t0 = time.time()
+    runner.spin(args.prewarm_ms)
+    runner.run(max(warmup_n, 3))
+    ms_total = timed(runner, steps_n, world, dev)
+    out = {"value": wpx * world * steps_n / (ms_total * 1e-3), "ms_per_step": ms_total / steps_n, "steps": steps_n,
+           "warped_px_per_step_per_gpu": wpx, "gpu_launches": steps[0].n_launches * steps_n,
+           "exchange": runner.exchange, "set_bytes": steps[0].bytes, "batch_per_gpu": Bl, "global_batch": Bg}
+    roof = None
+    if roofline:
+        dom = Runner(steps, args.graph_steps, 1, False, only=lambda s: s.dominant)
+        n_roof = min(200000, max(50, int(args.roofline_ms * 1e-3 / max(ms_total * 1e-3 / steps_n, 1e-6))))
+        dom.run(16)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        r0.record()
+        dom.run(n_roof)
+        r1.record()
+        torch.cuda.synchronize()
+        kernel_ms = r0.elapsed_time(r1) / n_roof
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        p = steps[0].dominant
+        bytes_launch = p.algorithmic_bytes()
+        achieved = bytes_launch / (kernel_ms * 1e-3) / 1e9
+        traffic, traffic_note = None, "no ncu capture recorded for this workload"
+        try:
+            tj = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+            ent = tj.get("workloads", {}).get(name)
+            if ent:
+                if ent.get("csrc_sha16") == csrc_sha16():
+                    traffic, traffic_note = ent["dram_bytes_per_launch"], ent.get("source")
+                else:
+                    traffic_note = "stale: profiles/traffic.json was captured with other kernel sources"
+        except Exception:
+            pass
+        kname = ("dvf::photo_loss_nhwc_kernel" if p.layout == 1 else "dvf::photo_loss_c3x2_kernel") + \
+            f"<V={p.V}, zeros, {'expl' if p.inputs[6] is not None else 'noexpl'}, grad> (dvf_photo_loss_fused_pose)"
+        roof = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_note,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 (B200_PROFILING.md)",
+                "algorithmic_bytes_per_launch": bytes_launch, "bytes_per_warped_px": bytes_launch / p.warped_px,
+                "kernel_us": kernel_ms * 1e3, "launches_timed": n_roof, "frac_of_nominal_8000": achieved / 8000.0}
+    if sampler:
+        sampler.mark(t0, time.time())
+    return out, roof, host, steps
+
+
+def e2e_leg(name, wl, args, world, dev, host, sampler):
+    """Public drop-in API with HOST inputs: every step uploads its inputs from pinned memory (the upload of step i+1
+    overlaps step i, the usual prefetching loader loop) and ends with a device -> host read of the loss."""
+    import torch.distributed as dist
+    import loss_functions as lf
+    import loss_functions_sfm as sfm
+    L, V = wl["levels"], wl["views"]
+    pin = lambda t: t.contiguous().pin_memory()   # noqa: E731
+    two_view = (L == 1 and V == 2)
+    hb = dict(tgt=pin(host["tgt"]), srcs=[pin(s) for s in host["srcs"]], pose=pin(host["pose"]), K=pin(host["K"]),
+              Ki=pin(host["Kinv"]), depths=[pin(x if two_view else x.unsqueeze(1)) for x in host["depths"]])
+    if wl["expl"]:
+        hb["expl"] = [pin(x) for x in host["expl"]]
+    if wl.get("feature"):
+        hb["feat"] = [pin(x) for x in host["feat"]]
+        hb["fdepth"], hb["fK"], hb["fKi"] = pin(host["feat_depth"]), pin(host["feat_K"]), pin(host["feat_Kinv"])
+
+    def flat(d):
+        for v in d.values():
+            if isinstance(v, list):
+                yield from v
+            else:
+                yield v
+    h2d = sum(t.numel() * t.element_size() for t in flat(hb))
+    copy_stream = torch.cuda.Stream()
+
+    def upload():
+        with torch.cuda.stream(copy_stream):
+            up = lambda t: t.to(dev, non_blocking=True)   # noqa: E731
+            bufs = {k: ([up(x) for x in v] if isinstance(v, list) else up(v)) for k, v in hb.items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return bufs, ev
+
+    def step(cur):
+        bufs, ev = cur
+        nxt = upload()
+        cs = torch.cuda.current_stream()
+        cs.wait_event(ev)
+        for t in flat(bufs):
+            t.record_stream(cs)
+        pose = bufs["pose"].requires_grad_(True)
+        depths = [x.requires_grad_(True) for x in bufs["depths"]]
+        if two_view:
+            loss = lf.photometric_reconstruction_loss(bufs["tgt"], bufs["srcs"][0], bufs["srcs"][1], depths[0], pose[:, 0],
+                                                      pose[:, 1], bufs["K"], bufs["Ki"])
+            if "feat" in bufs:
+                feats = [x.requires_grad_(True) for x in bufs["feat"]]
+                fd = bufs["fdepth"].requires_grad_(True)
+                loss = loss + lf.photometric_reconstruction_loss(feats[0], feats[1], feats[2], fd, pose[:, 0], pose[:, 1],
+                                                                 bufs["fK"], bufs["fKi"])
+        else:
+            masks = [x.requires_grad_(True) for x in bufs["expl"]] if "expl" in bufs else [None] * L
+            loss = sfm.photometric_reconstruction_loss(bufs["tgt"], bufs["srcs"], bufs["K"], bufs["Ki"], depths, masks, pose)
+        loss.backward()
+        loss.item()             # device -> host read of the step's result
+        return nxt
+
+    cur = upload()
+    for _ in range(3):
+        cur = step(cur)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_a = time.time()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    for _ in range(args.e2e_steps):
+        cur = step(cur)
+    q1.record()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.mark(t_a, time.time())
+    ems = torch.tensor([q0.elapsed_time(q1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    Bl = host["tgt"].shape[0]
+    return {"value": warped_px(wl, Bl) * world * args.e2e_steps / (float(ems.item()) * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": args.e2e_steps,
+            "ms_per_step": float(ems.item()) / args.e2e_steps,
+            "api": ("loss_functions.photometric_reconstruction_loss" if two_view else
+                    "loss_functions_sfm.photometric_reconstruction_loss") +
+                   "(...) + loss.backward() through the drop-in modules (area pyramid included); fp32 inputs in pinned host memory, "
+                   "step i+1's upload on a copy stream while step i computes, loss.item() every step"}
+
+
+def unfused_gpu_leg(wl, B, dev, seconds=3.0):
+    """The reference's own torch operator sequence (oracle/torch_port.py) on the SAME GPU, inputs resident: what
+    fusing buys over stock PyTorch-CUDA eager."""
+    step = torch_port_step_fn(wl, B, device=dev)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    n = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    while True:
+        for _ in range(5):
+            step()
+        n += 5
+        torch.cuda.synchronize()
+        if time.perf_counter() - t0 > seconds or n >= 500:
+            break
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": warped_px(wl, B) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": n, "batch": B,
+            "what": f"oracle/torch_port.py (the reference's torch op sequence, unfused) with torch {torch.__version__} CUDA eager on the same "
+                    "GPU, inputs resident, fwd+bwd (includes F.interpolate pyramids, as the reference's loss does)"}
+
+
+def run_b200(args):
+    import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,204 +630,56 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
-    sizes = [(H >> s, W >> s) for s in range(LEVELS)]
-    ds = [float(1 << s) for s in range(LEVELS)]
-
-    # ---- inputs: one CPU draw per rank, rotated into `sets` distinct device copies ----------------
-    host = make_inputs(B, seed=1000 + rank, smooth=not args.iid_depth)
-    plans, graphs, loss_graphs = [], [], []
-    for k in range(args.sets):
-        roll = lambda t: torch.roll(t, shifts=k, dims=0).contiguous().to(dev)   # noqa: E731
-        tgt_pyr = ops.area_pyramid(roll(host["tgt"]), sizes)
-        src_pyr = ops.area_pyramid(roll(host["src"]), sizes)
-        plan = FusedLossPlan(tgt_pyr, [[s] for s in src_pyr], [roll(x) for x in host["depths"]], roll(host["pose"]),
-                             roll(host["K"]), roll(host["Kinv"]), downscales=ds)
-        plans.append(plan)
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    round_graph = None
-    with torch.cuda.stream(side):
-        for p in plans:
-            graphs.append(p.capture())
-            loss_graphs.append(p.capture(loss_only=True))
-        if args.sets > 1 and not args.single_step_graphs:
-            # one graph = one ROUND of `sets` steps (one launch per input set), as a training iteration captured whole
-            # would hold them: consecutive steps are kernel -> kernel edges inside the graph instead of separate graph
-            # launches (~2 us of launch gap per step less).  Still one launch per step, K launches for K steps.
-            round_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(round_graph):
-                for p in plans:
-                    p.launch()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-
-    def run_steps(n, singles):
-        """n steps over the rotating input sets: whole rounds from the round graph, the rest one graph per step"""
-        i = 0
-        if round_graph is not None:
-            for _ in range(n // args.sets):
-                round_graph.replay()
-            i = (n // args.sets) * args.sets
-        for k in range(i, n):
-            singles[k % args.sets].replay()
-    wpx_step = plans[0].warped_px
-    bytes_launch = plans[0].algorithmic_bytes()
-    set_bytes = bytes_launch
-    assert wpx_step == warped_px(B)
-
+        t = torch.zeros(16, device=dev)
+        dist.all_reduce(t)          # communicator warm-up, untimed
+        torch.cuda.synchronize()
+    name, wl = args.config, WORKLOADS[args.config]
     sampler = ClockSampler(local) if rank == 0 else None
 
-    def spin(graph_list, ms):
-        t_end = time.perf_counter() + ms / 1e3
-        i = 0
-        while time.perf_counter() < t_end:
-            for _ in range(32):
-                graph_list[i % len(graph_list)].replay()
-                i += 1
-            torch.cuda.synchronize()
-        return i
-
-    # ---- value: K steps, device-timed, max over ranks ----------------------------------------------
-    t_load0 = time.time()
-    spin(graphs, args.prewarm_ms)
-    for i in range(args.warmup):
-        graphs[i % args.sets].replay()
-    acc_terms = torch.zeros_like(plans[0].terms)
-    torch.cuda.synchronize()
+    main, roof, host, steps = measure_workload(name, wl, args, world, rank, dev, sampler, args.steps, args.warmup)
+    e2e = None if args.no_e2e else e2e_leg(name, wl, args, world, dev, host, sampler)
+    Bl = main["batch_per_gpu"]
+    del steps
+    extras = {}
+    if not args.no_extras and name == "C2":
+        # strong scaling on C3 at a fixed global batch of 256 (BASELINE configs[2]), same run, same GPUs
+        c3 = WORKLOADS["C3"]
+        s_out, s_roof, _, s_steps = measure_workload("C3", c3, args, world, rank, dev, sampler, args.steps, args.warmup)
+        del s_steps
+        extras["strong_c3"] = {"metric": METRIC, "value": s_out["value"], "unit": UNIT, "scaling": "strong", "n_gpus": world,
+                               "ms_per_step": s_out["ms_per_step"], "steps": s_out["steps"], "global_batch": s_out["global_batch"],
+                               "batch_per_gpu": s_out["batch_per_gpu"], "exchange": s_out["exchange"],
+                               "workload": c3["title"], "roofline": s_roof}
+    if not args.no_extras and rank == 0:
+        try:
+            extras["unfused_gpu"] = unfused_gpu_leg(wl, Bl, dev)
+        except Exception as e:   # e.g. out of memory on the large shapes: the fused path does not depend on it
+            extras["unfused_gpu"] = {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
+        torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
-        torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run_steps(args.steps, graphs)
-    if world > 1:
-        acc_terms.copy_(plans[(args.steps - 1) % args.sets].terms)
-        dist.all_reduce(acc_terms)     # the only exchange of the path: <= 16 floats of loss terms
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    value = wpx_step * world * args.steps / (ms_total * 1e-3)
-
-    # ---- roofline: the dominant kernel alone, CUDA events on its launch stream --------------------
-    n_roof = max(50, int(args.roofline_ms * 1e-3 / max(ms_total * 1e-3 / args.steps, 1e-6)))
-    n_roof = min(n_roof, 200000)
-    for i in range(10):
-        loss_graphs[i % args.sets].replay()
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    r0.record()
-    run_steps(n_roof, loss_graphs)
-    r1.record()
-    torch.cuda.synchronize()
-    t_load1 = time.time()
-    if sampler:
-        sampler.mark(t_load0, t_load1)
-    kernel_ms = r0.elapsed_time(r1) / n_roof
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = bytes_launch / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get("photo_loss_kernel_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "dvf::photo_loss_c3x2_kernel<1,zeros,noexpl,grad,tma> (dvf_photo_loss_fused_pose)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 (B200_PROFILING.md)",
-                "algorithmic_bytes_per_launch": bytes_launch, "bytes_per_warped_px": bytes_launch / wpx_step,
-                "kernel_us": kernel_ms * 1e3, "launches_timed": n_roof, "frac_of_nominal_8000": achieved / 8000.0}
-
-    # ---- e2e: public drop-in API, inputs from pinned host memory every step ------------------------
-    e2e = None
-    if not args.no_e2e:
-        import loss_functions_sfm as sfm
-        pin = lambda t: t.contiguous().pin_memory()   # noqa: E731
-        h_t, h_s = pin(host["tgt"]), pin(host["src"])
-        h_d = [pin(x.unsqueeze(1)) for x in host["depths"]]
-        h_p, h_K, h_Ki = pin(host["pose"]), pin(host["K"]), pin(host["Kinv"])
-        h2d = sum(t.numel() * 4 for t in [h_t, h_s, h_p, h_K, h_Ki] + h_d)
-
-        # Inputs of step i+1 are uploaded on a copy stream while step i computes (the usual prefetching loader loop);
-        # every step's inputs cross PCIe once, inside the timed region, and every step ends with a D2H read of its loss.
-        copy_stream = torch.cuda.Stream()
-
-        def upload():
-            with torch.cuda.stream(copy_stream):
-                up = lambda t: t.to(dev, non_blocking=True)   # noqa: E731
-                bufs = dict(tgt=up(h_t), src=up(h_s), depths=[up(x) for x in h_d], pose=up(h_p), K=up(h_K), Ki=up(h_Ki))
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return bufs, ev
-
-        def e2e_step(cur):
-            bufs, ev = cur
-            nxt = upload()                                   # step i+1's H2D overlaps this step's kernels
-            cs = torch.cuda.current_stream()
-            cs.wait_event(ev)
-            for t in [bufs["tgt"], bufs["src"], bufs["pose"], bufs["K"], bufs["Ki"]] + bufs["depths"]:
-                t.record_stream(cs)
-            depths = [x.requires_grad_(True) for x in bufs["depths"]]
-            pose = bufs["pose"].requires_grad_(True)
-            loss = sfm.photometric_reconstruction_loss(bufs["tgt"], [bufs["src"]], bufs["K"], bufs["Ki"], depths,
-                                                       [None] * LEVELS, pose)
-            loss.backward()
-            loss.item()             # device -> host read of the step's result
-            return nxt
-
-        cur = upload()
-        for _ in range(3):
-            cur = e2e_step(cur)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t_a = time.time()
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        q0.record()
-        for _ in range(args.e2e_steps):
-            cur = e2e_step(cur)
-        q1.record()
-        torch.cuda.synchronize()
-        if sampler:
-            sampler.mark(t_a, time.time())
-        ems = torch.tensor([q0.elapsed_time(q1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": wpx_step * world * args.e2e_steps / (float(ems.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": args.e2e_steps,
-               "api": "loss_functions_sfm.photometric_reconstruction_loss(...) + loss.backward() (includes the area pyramid); "
-                      "pinned-host inputs of step i+1 uploaded on a copy stream while step i computes, loss.item() every step"}
-
     clocks = sampler.finish() if sampler else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.cpu_seconds, args.cpu_batch)
+        cpu = cpu_baseline(wl, args.cpu_seconds, args.cpu_batch or min(Bl, 64))
 
     if rank == 0:
+        cfg = config_dict(name, wl, world, args)
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: 4-scale stereo photometric loss fwd+bwd, batch 64/GPU at 128x416 (BASELINE configs[1])",
-                       "batch_per_gpu": B, "global_batch": B * world, "levels": LEVELS, "views": 1, "layout": "NCHW fp32",
-                       "depth_field": "iid-noise (stress)" if args.iid_depth else "smooth (17x17 box-filtered disparity)",
-                       "pyramid": "prebuilt inputs (SURVEY 8d)", "parallelism": f"batch-sharded dp{world}",
-                       "l2_policy": f"{args.sets} rotating input sets, {args.sets * set_bytes / 1e6:.0f} MB > 126 MB L2",
-                       "step": "ONE launch: dvf_photo_loss_fused_pose (pose_vec2mat+projection, warp+loss+all gradients over 4 levels, pose backward); "
-                               + ("CUDA graph per step" if round_graph is None else f"CUDA graphs of {args.sets} consecutive steps (one per input set)")},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": plans[0].n_launches * args.steps,
-            "warped_px_per_step_per_gpu": wpx_step,
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "detail": {"l2_policy": f"{args.sets} rotating input sets, {args.sets * main['set_bytes'] / 1e6:.0f} MB > 126 MB L2",
+                       "step": f"{main['gpu_launches'] // args.steps} launch(es) of dvf_photo_loss_fused_pose per step (pose_vec2mat + "
+                               f"projection, warp + loss + all gradients over all levels and views, pose backward); CUDA graphs of "
+                               f"{args.graph_steps} consecutive steps" + ("" if (args.no_pdl or args.sets < 2) else
+                               "; consecutive steps work on disjoint input sets and are chained by programmatic dependent launch "
+                               "(DVF_FLAG_PDL): the serial tail of step i overlaps the pixel work of step i+1"),
+                       "exchange": main["exchange"]},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": main["gpu_launches"], "warped_px_per_step_per_gpu": main["warped_px_per_step_per_gpu"],
         }
+        out.update(extras)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -6,8 +6,6 @@
 // Device code: dvf_loss_kernel.cuh (instantiated in dvf_loss_inst_*.cu so the variants build in parallel).
 // Roofline: HBM-bound stream (no dense contraction => no tensor cores); algorithmic traffic
 // (4 + 4C + 4)/V + 4C bytes per warped pixel for fp32 NCHW (32 B at C=3, V=1).
-#include <stdlib.h>
-
 #include "dvf_loss_nhwc.cuh"
 
 namespace dvf {
@@ -63,9 +61,8 @@ static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) 
     // fixed cost of a piece in units.  Image kernel, measured on C2 (V = 1): 2 -> 73.7 us, 3 -> 69.6, 4 -> 67.4,
     // 5 -> 67.4, 6 -> 68.5, 8 -> 69.7; with V = 2 a unit is twice the work: 3 -> 120.1 us, 4 -> 122.6, 6 -> 125.4.
     // A unit of the channels-last kernel is C/kVec times more work again, so its pieces cost less than one unit.
-    const char* e = getenv("DVF_PIECE_OVERHEAD");   // tuning aid
     const int by_views = d->V == 1 ? 4 : (d->V == 2 ? 3 : 2);
-    pl.piece_overhead = (e && atoi(e) >= 0) ? atoi(e) : (d->layout == DVF_NHWC ? 0 : by_views);
+    pl.piece_overhead = d->piece_overhead > 0 ? d->piece_overhead : (d->layout == DVF_NHWC ? 0 : by_views);
   }
   long long per_image = 0;
   for (int l = 0; l < d->n_levels; ++l) {
@@ -167,6 +164,16 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     prm.gvec = pose->gvec;
   }
   prm.terms = terms;
+  if (d->mean_batch < 0 || (d->mean_batch > 0 && d->mean_batch < d->B)) return DVF_EINVAL_SHAPE;
+  const int mean_batch = d->mean_batch > 0 ? d->mean_batch : d->B;
+  prm.mean_batch = mean_batch;
+  prm.upstream = d->upstream;
+  prm.nan_flags = (d->flags & DVF_FLAG_NAN_CHECK) ? d->nan_flags : nullptr;
+  if ((d->flags & DVF_FLAG_NAN_CHECK) && !d->nan_flags) return DVF_EINVAL_NULL;
+  prm.ctas_per_sm = d->ctas_per_sm;
+  prm.pdl = (d->flags & DVF_FLAG_PDL) ? 1 : 0;
+  if (d->grad_dtype != DVF_F32) return DVF_EUNSUPPORTED;   // TODO bf16 map gradients
+  prm.grad_bf16 = d->grad_dtype == DVF_BF16;
   bool need_grad = false;
   char* ws = static_cast<char*>(workspace);
   for (int l = 0; l < d->n_levels; ++l) {
@@ -180,10 +187,10 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     t.W = s.W;
     t.HW = s.H * s.W;
     t.divW = make_fastdiv((uint32_t)s.W);
-    t.geo = make_geo(s.H, s.W);
+    t.geo = make_geo(s.H, s.W, (d->flags & DVF_FLAG_ALIGN_CORNERS) != 0);
     t.allow_fast = (s.W > 1 && s.H > 1 && s.W <= 32768 && s.H <= 32768);
     t.ds = pose ? pose->downscale[l] : 1.0f;
-    t.inv_n = 1.0f / (float)((double)d->B * d->C * s.H * s.W);
+    t.inv_n = 1.0f / (float)((double)mean_batch * d->C * s.H * s.W);
     t.depth = s.depth;
     t.tgt = static_cast<const float*>(s.tgt);
     t.expl = s.expl;
@@ -219,6 +226,15 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
   prm.gM_ws = reinterpret_cast<double*>(ws + pl.off_gM);
   prm.pose_counter = reinterpret_cast<unsigned*>(ws + pl.off_pcnt);
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  if (d->flags & DVF_FLAG_ZERO_GSRC) {
+    const size_t gesz = d->grad_dtype == DVF_BF16 ? 2 : 4;
+    for (int l = 0; l < d->n_levels; ++l)
+      for (int v = 0; v < d->V; ++v)
+        if (levels[l].gsrc[v]) {
+          const cudaError_t e = cudaMemsetAsync(levels[l].gsrc[v], 0, (size_t)d->B * d->C * levels[l].H * levels[l].W * gesz, cs);
+          if (e != cudaSuccess) return (int)e;
+        }
+  }
   prm.total_units = (int)pl.total_units;
   prm.units_per_image_all = pl.units_per_image_all;
   prm.piece_overhead = pl.piece_overhead;
@@ -251,7 +267,7 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     for (int l = 0; l < d->n_levels; ++l)
       if (expl && !levels[l].expl) return DVF_EINVAL_NULL;   // all levels or none
     // bulk-copy (TMA) path: contiguous runs must start on 16-byte boundaries for every image and level
-    bool tma = getenv("DVF_NO_TMA") == nullptr;
+    bool tma = (d->flags & DVF_FLAG_NO_TMA) == 0;
     for (int l = 0; l < d->n_levels; ++l) {
       const dvf_level& s = levels[l];
       tma = tma && ((s.H * s.W) % 4 == 0) && aligned(s.depth, 16) && aligned(s.tgt, 16);

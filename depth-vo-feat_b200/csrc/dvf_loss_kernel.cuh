@@ -17,8 +17,6 @@
 //     butterfly, then per piece, and the LAST piece of an image (atomic ticket) adds the partials in
 //     a fixed order in fp64 -> deterministic, no output needs pre-zeroing, no second launch.
 #pragma once
-#include <stdlib.h>
-
 #include <type_traits>
 
 #include "dvf_internal.h"
@@ -72,6 +70,12 @@ struct LossParams {
   int units_per_image_all; // units of one image over all levels, overhead units included
   int piece_overhead;      // empty units in front of every (image, level)
   float* terms;  // [n_levels*V]
+  int mean_batch;          // batch size in the denominators (>= B: this launch may hold a shard of a larger batch)
+  int ctas_per_sm;         // > 0: grid override of the balanced kernels (tuning)
+  int grad_bf16;           // NHWC bf16 maps: map gradients are bf16
+  int pdl;                 // programmatic dependent launch (DVF_FLAG_PDL)
+  const float* upstream;   // device scalar multiplying every gradient, or nullptr (= 1)
+  int* nan_flags;          // nullptr, or a word that collects bit l*V+v when term (l, v) is NaN
   // pose mode (dvf_photo_loss_fused_pose): P / K^-1_s are derived in the CTA prologue, d pose in the epilogue
   const float* pose_vec;   // [B,V,6] or nullptr
   const float* K;          // [B,3,3]
@@ -168,6 +172,20 @@ __device__ __forceinline__ void load_matrices(const LossParams& prm, const Level
   } else {
     if (tid < kV * 12) s_P[tid / 12][tid % 12] = lv.P[((size_t)b * kV + tid / 12) * 12 + tid % 12];
     if (tid >= 64 && tid < 73) s_M[tid - 64] = lv.Kinv[b * 9 + (tid - 64)];
+  }
+}
+
+// Programmatic dependent launch (DVF_FLAG_PDL): every CTA lets the NEXT kernel of the stream be scheduled as soon as
+// SM slots free up, and waits for the PREVIOUS kernel to have completed (memory flushed) before it first touches the
+// workspace -- partial sums and ticket counters may be shared with it.  Inputs are read and gradient maps written
+// before that (contract in include/dvf_b200.h).  Both instructions are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_let_successor_start(const LossParams& prm) {
+  if (prm.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_predecessor(const LossParams& prm, bool& done) {
+  if (prm.pdl && !done) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    done = true;
   }
 }
 
@@ -288,7 +306,9 @@ __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], c
         if (tid == 0) {
           double t = 0.0;
           for (int w8 = 0; w8 < kThreadsT / 32; ++w8) t += s_term[w8];
-          prm.terms[l * kV + v] = (float)(t / ((double)prm.B * (double)C * (double)lv.HW));
+          const float term = (float)(t / ((double)prm.mean_batch * (double)C * (double)lv.HW));
+          prm.terms[l * kV + v] = term;
+          if (prm.nan_flags && term != term) atomicOr(prm.nan_flags, 1 << ((l * kV + v) & 31));
         }
         __syncthreads();
       }
@@ -362,6 +382,8 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   int w = (int)((long long)blockIdx.x * T / G);
   const int w_end = (int)(((long long)blockIdx.x + 1) * T / G);
   int ring_k = 0;   // chunks this CTA has pushed through the ring so far (stage / parity bookkeeping)
+  pdl_let_successor_start(prm);
+  bool pdl_waited = false;
 
   while (w < w_end) {
   const int b = w / prm.units_per_image_all;
@@ -381,7 +403,7 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   const Geo geo = lv.geo;
   const Geo2 geo2 = make_geo2(geo);
   const FastDiv divW = lv.divW;
-  const float inv_n = lv.inv_n;
+  const float inv_n = prm.upstream ? mul(lv.inv_n, __ldg(prm.upstream)) : lv.inv_n;
 
   f2 acc2[kV][12];     // dL/dP partial sums, (A,B) lanes folded at the end
   float accl[kV];      // loss partial sums
@@ -685,6 +707,7 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
     acc[v][12] = accl[v];
     acc[v][13] = acc[v][14] = acc[v][15] = 0.0f;
   }
+  pdl_wait_predecessor(prm, pdl_waited);
   reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, part, n_parts, b, kC);
   }  // pieces of this CTA
 }
@@ -710,7 +733,7 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_cn_kernel(const __
   const bool need_grad = prm.need_grad != 0;
   const bool allow_fast = lv.allow_fast != 0;
   const bool has_expl = lv.expl != nullptr;
-  const float inv_n = lv.inv_n;
+  const float inv_n = prm.upstream ? mul(lv.inv_n, __ldg(prm.upstream)) : lv.inv_n;
 
   load_matrices<kV>(prm, lv, b, s_P, s_M);
   __syncthreads();
@@ -830,20 +853,31 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_cn_kernel(const __
 }
 
 // Launch of the image kernel: one CTA per resident slot of this variant (occupancy query, cached per variant), every
-// CTA an equal share of the units => a single wave without a tail.  DVF_CTAS_PER_SM overrides (tuning aid).
+// CTA an equal share of the units => a single wave without a tail.  dvf_loss_desc.ctas_per_sm overrides (tuning aid).
 template <void (*kKernel)(const LossParams)>
 inline void launch_balanced(const LossParams& prm, int cap, cudaStream_t st) {
   static int per_sm = 0;   // benign race: every thread computes the same value
   if (per_sm == 0) {
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kKernel, kLossThreads, 0) != cudaSuccess || n < 1) n = 1;
-    const char* e = getenv("DVF_CTAS_PER_SM");
-    if (e && atoi(e) > 0) n = atoi(e);
     per_sm = n;
   }
-  long long g = (long long)per_sm * num_sms();
+  long long g = (long long)(prm.ctas_per_sm > 0 ? prm.ctas_per_sm : per_sm) * num_sms();
   if (g > cap) g = cap;
   if (g > prm.total_units) g = prm.total_units;
+  if (prm.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)g);
+    cfg.blockDim = dim3(kLossThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kKernel, prm);
+    return;
+  }
   kKernel<<<(int)g, kLossThreads, 0, st>>>(prm);
 }
 

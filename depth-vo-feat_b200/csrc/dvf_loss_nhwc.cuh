@@ -148,6 +148,8 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
   const int G = (int)gridDim.x, T = prm.total_units;
   int w = (int)((long long)blockIdx.x * T / G);
   const int w_end = (int)(((long long)blockIdx.x + 1) * T / G);
+  pdl_let_successor_start(prm);
+  bool pdl_waited = false;
   while (w < w_end) {
   const int b = w / prm.units_per_image_all;
   int l = 0;
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
   const Geo geo = lv.geo;
   const bool allow_fast = lv.allow_fast != 0;
   const bool has_expl = lv.expl != nullptr;
-  const float inv_n = lv.inv_n;
+  const float inv_n = prm.upstream ? mul(lv.inv_n, __ldg(prm.upstream)) : lv.inv_n;
 
   load_matrices<kV>(prm, lv, b, s_P, s_M);
   __syncthreads();
@@ -405,6 +407,7 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
     acc[v][12] = acc_loss[v];
     acc[v][13] = acc[v][14] = acc[v][15] = 0.0f;
   }
+  pdl_wait_predecessor(prm, pdl_waited);
   reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, part, n_parts, b, C);
   }  // pieces of this CTA
 }

@@ -45,6 +45,7 @@ struct Geo2 {          // per-level constants, both halves equal
   f2 nW1, nH1;         // -(W-1), -(H-1)
   f2 rW1, rH1;         // correctly rounded reciprocals
   f2 halfW, halfH;
+  f2 offs;
 };
 __device__ __forceinline__ Geo2 make_geo2(const Geo& g) {
   Geo2 o;
@@ -54,6 +55,7 @@ __device__ __forceinline__ Geo2 make_geo2(const Geo& g) {
   o.rH1 = dup(g.rH1);
   o.halfW = dup(g.halfW);
   o.halfH = dup(g.halfH);
+  o.offs = dup(g.offs);
   return o;
 }
 
@@ -113,9 +115,9 @@ struct Loc2 {
 
 template <bool kZeros>
 __device__ __forceinline__ void locate2(f2 xn, f2 yn, int H, int W, const Geo& gs, const Geo2& g, Loc2& L) {
-  const f2 one = dup(1.0f), mhalf = dup(-0.5f);
-  f2 ix = fma2(add2(xn, one), g.halfW, mhalf);
-  f2 iy = fma2(add2(yn, one), g.halfH, mhalf);
+  const f2 one = dup(1.0f);
+  f2 ix = fma2(add2(xn, one), g.halfW, g.offs);
+  f2 iy = fma2(add2(yn, one), g.halfH, g.offs);
   L.gmx = g.halfW;
   L.gmy = g.halfH;
   if (!kZeros) {  // border padding: clip_coordinates(_set_grad)

@@ -443,7 +443,7 @@ static int fill_params(const dvf_desc* d, WarpParams& p) {
   p.W = d->W;
   p.HW = d->H * d->W;
   p.divW = make_fastdiv((uint32_t)d->W);
-  p.geo = make_geo(d->H, d->W);
+  p.geo = make_geo(d->H, d->W, (d->flags & DVF_FLAG_ALIGN_CORNERS) != 0);
   p.allow_fast = d->W > 1 && d->H > 1;
   p.zeros_padding = d->padding == DVF_PAD_ZEROS;
   p.blocks_per_image = (p.HW + kThreads * kWarpPPT - 1) / (kThreads * kWarpPPT);

@@ -17,6 +17,8 @@ F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
 PADDING = {"zeros": 0, "border": 1}
 ROTATION = {"euler": 0, "quat": 1}
+FLAG_ALIGN_CORNERS, FLAG_ZERO_GSRC, FLAG_NAN_CHECK, FLAG_NO_TMA, FLAG_PDL = 1, 2, 4, 8, 16
+ABI_VERSION = 2
 
 
 class DvfError(RuntimeError):
@@ -25,7 +27,7 @@ class DvfError(RuntimeError):
 
 class dvf_desc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("dtype", C.c_int32), ("layout", C.c_int32), ("padding", C.c_int32), ("reserved", C.c_int32)]
+                ("dtype", C.c_int32), ("layout", C.c_int32), ("padding", C.c_int32), ("flags", C.c_int32)]
 
 
 class dvf_level(C.Structure):
@@ -49,7 +51,9 @@ class dvf_reg_level(C.Structure):
 
 class dvf_loss_desc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("V", C.c_int32), ("n_levels", C.c_int32),
-                ("dtype", C.c_int32), ("layout", C.c_int32), ("padding", C.c_int32), ("reserved", C.c_int32)]
+                ("dtype", C.c_int32), ("layout", C.c_int32), ("padding", C.c_int32), ("flags", C.c_int32),
+                ("mean_batch", C.c_int32), ("grad_dtype", C.c_int32), ("piece_overhead", C.c_int32), ("ctas_per_sm", C.c_int32),
+                ("upstream", C.c_void_p), ("nan_flags", C.c_void_p)]
 
 
 _vp, _i32, _sz, _fp = C.c_void_p, C.c_int32, C.c_size_t, C.POINTER(C.c_float)
@@ -112,8 +116,8 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the .so is stale: loud by design
         fn.restype = res
         fn.argtypes = args
-    if lib.dvf_version() != 1:
-        raise DvfError(f"{path}: ABI version {lib.dvf_version()} != 1; rebuild with DVF_REBUILD=1")
+    if lib.dvf_version() != ABI_VERSION:
+        raise DvfError(f"{path}: ABI version {lib.dvf_version()} != {ABI_VERSION}; rebuild with DVF_REBUILD=1")
     _lib = lib
     return lib
 

@@ -119,17 +119,44 @@ def _req_maps(maps, name):
 
 
 def workspace(nbytes: int, device: torch.device, signature) -> torch.Tensor:
-    """Zero-initialised scratch, one per (device, stream, call signature).  The kernels restore the
-    ticket counters they use, so a workspace is reusable by later calls WITH THE SAME SHAPES; a call
-    with other shapes lays the counters out elsewhere and therefore gets its own buffer."""
-    key = (device.index, _stream(), signature)
+    """Zero-initialised scratch, one per (device, stream, size, call signature).  The kernels restore the
+    ticket counters they use, so a workspace is reusable by later calls WITH THE SAME PLAN on the same stream
+    (launches on one stream are serialised); anything that changes the plan -- shapes, layout, element type,
+    view count, tuning fields -- must be part of `signature`, because another plan lays the counters out
+    elsewhere.  `drop_workspace` forgets a buffer whose launch failed (its counters may be dirty)."""
+    key = (device.index, _stream(), int(nbytes), signature)
     ws = _WS.get(key)
-    if ws is None or ws.numel() < nbytes:
+    if ws is None:
         if len(_WS) > 64:
-            _WS.clear()
+            _WS.clear()     # stream-ordered allocator: in-flight kernels keep their memory until they finish
         ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
         _WS[key] = ws
     return ws
+
+
+def drop_workspace(ws: torch.Tensor):
+    for k in [k for k, v in _WS.items() if v is ws]:
+        del _WS[k]
+
+
+def _checked(status: int, what: str, ws: Optional[torch.Tensor] = None):
+    if status != 0 and ws is not None:
+        drop_workspace(ws)
+    _lib.check(status, what)
+
+
+def _same_device(*tensors):
+    """All tensors of a call live on one CUDA device; returns a context that makes it current (the library
+    launches on the current device's stream)."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise DvfError(f"tensors of one call are on different devices ({dev} and {t.device})")
+    return torch.cuda.device(dev)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -182,9 +209,19 @@ class PoseVec2Mat(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # inverse_warp
 # ------------------------------------------------------------------------------------------------
-def _desc(img, padding_mode):
+# F.grid_sample convention of every sampling entry.  False = torch >= 1.3's default, which is what the reference runs
+# with today (inverse_warp.py:191 passes nothing); True = the torch <= 1.2 behaviour the reference was written for.
+ALIGN_CORNERS = False
+
+
+def _flags(align_corners=None):
+    ac = ALIGN_CORNERS if align_corners is None else align_corners
+    return _lib.FLAG_ALIGN_CORNERS if ac else 0
+
+
+def _desc(img, padding_mode, align_corners=None):
     B, Cc, H, W = img.shape
-    return dvf_desc(B, Cc, H, W, _lib.F32, _lib.NCHW, PADDING[padding_mode], 0)
+    return dvf_desc(B, Cc, H, W, _lib.F32, _lib.NCHW, PADDING[padding_mode], _flags(align_corners))
 
 
 def inverse_warp_fwd_P(img, depth, P, Kinv, padding_mode="zeros", want_valid=False):
@@ -315,23 +352,148 @@ def area_pyramid(img, sizes: Sequence[Sequence[int]]):
 # fused reconstruction loss
 # ------------------------------------------------------------------------------------------------
 class _LossCfg:
-    __slots__ = ("V", "L", "rotation_mode", "padding_mode", "downscales", "has_expl", "expl_channels")
+    __slots__ = ("V", "L", "rotation_mode", "padding_mode", "downscales", "has_expl", "expl_channels", "align_corners",
+                 "global_batch", "nan_check")
 
 
-def _scale_inplace(tensors: List[torch.Tensor], g: torch.Tensor):
-    ts = [t for t in tensors if t is not None]
-    if not ts:
-        return
-    try:
-        torch._foreach_mul_(ts, g)
-    except Exception:  # older foreach signatures
-        for t in ts:
-            t.mul_(g)
+def _scaled(tensors: List[Optional[torch.Tensor]], g: torch.Tensor):
+    """[t * g] out of place (the unit gradients stay valid for another backward call, retain_graph=True)."""
+    idx = [i for i, t in enumerate(tensors) if t is not None]
+    out = [None] * len(tensors)
+    if idx:
+        for i, r in zip(idx, torch._foreach_mul([tensors[i] for i in idx], g)):
+            out[i] = r
+    return out
+
+
+_NAN_WORDS = {}
+
+
+def nan_flags(device=None) -> torch.Tensor:
+    """The device word the loss kernels OR NaN bits into when nan_check is on (bit l*V+v <-> terms[l*V+v]); one per
+    device.  Reading it (`.item()`) is the only synchronisation, and the caller chooses when."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    w = _NAN_WORDS.get(dev.index)
+    if w is None:
+        w = torch.zeros(1, dtype=torch.int32, device=dev)
+        _NAN_WORDS[dev.index] = w
+    return w
+
+
+class _LossCall:
+    """One validated loss call: prepared tensors + which gradients are wanted; can launch the fused kernel
+    forward-only or forward+backward (any number of times)."""
+
+    def __init__(self, cfg, pose, K, Kinv, tensors, needs):
+        V, L = cfg.V, cfg.L
+        self.cfg = cfg
+        self.pose = _req(pose, "pose", 3)
+        self.K, self.Kinv = _req(K, "intrinsics", 3), _req(Kinv, "intrinsics_inv", 3)
+        maps, self.layout, self.dtype = _req_maps(list(tensors[0:L + L * V]), "tgt/src")
+        self.tgts, self.srcs = maps[0:L], maps[L:L + L * V]
+        self.in_dtypes = [t.dtype for t in tensors[0:L + L * V]]
+        self.depths = [_req(t, "depth", 3) for t in tensors[L + L * V:2 * L + L * V]]
+        self.expls = [_req(t, "explainability_mask", 4) for t in tensors[2 * L + L * V:]] if cfg.has_expl else []
+        off = 4  # index of the first *tensors entry in needs_input_grad
+        self.need_pose = needs[1]
+        self.need_tgt = [needs[off + i] for i in range(L)]
+        self.need_src = [needs[off + L + i] for i in range(L * V)]
+        self.need_depth = [needs[off + L + L * V + i] for i in range(L)]
+        self.need_expl = [needs[off + 2 * L + L * V + i] for i in range(L)] if cfg.has_expl else [False] * L
+        self.B, self.C = self.tgts[0].shape[0], self.tgts[0].shape[1]
+        for l in range(L):
+            h, w = self.depths[l].shape[1], self.depths[l].shape[2]
+            if self.tgts[l].shape != (self.B, self.C, h, w):
+                raise AssertionError(f"level {l}: target {list(self.tgts[l].shape)} does not match depth {list(self.depths[l].shape)}")
+            for v in range(V):
+                if self.srcs[l * V + v].shape != self.tgts[l].shape:
+                    raise AssertionError(f"level {l} view {v}: source {list(self.srcs[l * V + v].shape)} != target "
+                                         f"{list(self.tgts[l].shape)}")
+            if cfg.has_expl:
+                e = self.expls[l]
+                if e.shape[0] != self.B or e.shape[1] < V or e.shape[2:] != (h, w):
+                    raise AssertionError(f"level {l}: explainability mask {list(e.shape)} does not match depth")
+        self.any_map_grad = any(self.need_tgt) or any(self.need_src)
+        self.any_grad = self.any_map_grad or self.need_pose or any(self.need_depth) or any(self.need_expl)
+
+    def run(self, want_grads: bool, upstream: Optional[torch.Tensor] = None):
+        """-> (terms [L*V], grads | None) with grads = [pose] + tgt(L) + src(L*V) + depth(L) (+ expl(L))."""
+        lib = _lib.load()
+        cfg, V, L, B, Cc = self.cfg, self.cfg.V, self.cfg.L, self.B, self.C
+        dev = self.pose.device
+        with _same_device(self.pose, self.K, self.Kinv, *self.tgts, *self.srcs, *self.depths, *self.expls):
+            vec = self.pose.reshape(B * V, 6)
+            # the kernel derives P and K^-1_s from the pose itself and finishes with the pose backward (one launch);
+            # dP is only materialised for the pose gradient, inside the kernel's workspace
+            g_pose = torch.empty(B, V, 6, device=dev, dtype=torch.float32) if (want_grads and self.need_pose) else None
+            ds_arr = (C.c_float * L)(*[float(x) for x in cfg.downscales])
+            pargs = dvf_pose_args(vec.data_ptr(), self.K.data_ptr(), self.Kinv.data_ptr(), ds_arr, ROTATION[cfg.rotation_mode],
+                                  0, _ptr(g_pose))
+            terms = torch.empty(L * V, device=dev, dtype=torch.float32)
+            levels = (dvf_level * L)()
+            g_tgt, g_src, g_depth, g_expl = [None] * L, [None] * (L * V), [None] * L, [None] * L
+            for l in range(L):
+                lv = levels[l]
+                h, w = self.depths[l].shape[1], self.depths[l].shape[2]
+                lv.H, lv.W = h, w
+                lv.depth, lv.tgt = self.depths[l].data_ptr(), self.tgts[l].data_ptr()
+                for v in range(V):
+                    sv = self.srcs[l * V + v]
+                    lv.src[v] = sv.data_ptr()
+                    if want_grads and self.need_src[l * V + v]:
+                        g_src[l * V + v] = torch.empty_like(sv, dtype=torch.float32)   # zero-filled by the entry (DVF_FLAG_ZERO_GSRC)
+                        lv.gsrc[v] = g_src[l * V + v].data_ptr()
+                if cfg.has_expl:
+                    e = self.expls[l]
+                    lv.expl, lv.expl_bstride = e.data_ptr(), e.shape[1] * h * w
+                    if want_grads and self.need_expl[l]:
+                        # dense [B,V,h,w]; channels >= V of a wider mask get zero gradient
+                        g_expl[l] = torch.empty(B, V, h, w, device=dev, dtype=torch.float32)
+                        lv.gexpl = g_expl[l].data_ptr()
+                if want_grads and self.need_depth[l]:
+                    g_depth[l] = torch.empty_like(self.depths[l])
+                    lv.gdepth = g_depth[l].data_ptr()
+                if want_grads and self.need_tgt[l]:
+                    g_tgt[l] = torch.empty_like(self.tgts[l], dtype=torch.float32)
+                    lv.gtgt = g_tgt[l].data_ptr()
+            flags = _flags(cfg.align_corners) | _lib.FLAG_ZERO_GSRC | (_lib.FLAG_NAN_CHECK if cfg.nan_check else 0)
+            up = None
+            if upstream is not None:
+                up = upstream.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+            d = dvf_loss_desc(B, Cc, V, L, self.dtype, self.layout, PADDING[cfg.padding_mode], flags,
+                              int(cfg.global_batch or 0), _lib.F32, 0, 0, _ptr(up),
+                              nan_flags(dev).data_ptr() if cfg.nan_check else None)
+            nbytes = lib.dvf_photo_loss_workspace_bytes(C.byref(d), levels)
+            if nbytes == 0:
+                raise DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")
+            ws = workspace(nbytes, dev, ("loss", B, Cc, V, cfg.has_expl, self.layout, self.dtype) +
+                           tuple(tuple(x.shape[1:]) for x in self.depths))
+            _checked(lib.dvf_photo_loss_fused_pose(C.byref(d), levels, C.byref(pargs), _ptr(terms), _ptr(ws), ws.numel(),
+                                                   _stream()), "dvf_photo_loss_fused_pose", ws)
+            if not want_grads:
+                return terms, None
+            for l in range(L):
+                if cfg.has_expl and self.need_expl[l] and self.expls[l].shape[1] > V:
+                    full = torch.zeros_like(self.expls[l])
+                    full[:, :V] = g_expl[l]
+                    g_expl[l] = full
+            # gradients of the maps go back in the dtype the caller handed in
+            g_tgt = [g if g is None or g.dtype == self.in_dtypes[i] else g.to(self.in_dtypes[i]) for i, g in enumerate(g_tgt)]
+            g_src = [g if g is None or g.dtype == self.in_dtypes[L + i] else g.to(self.in_dtypes[L + i])
+                     for i, g in enumerate(g_src)]
+            return terms, [g_pose] + g_tgt + g_src + g_depth + (g_expl if cfg.has_expl else [])
 
 
 class FusedPhotoLoss(torch.autograd.Function):
-    """sum over levels and views of mean|(tgt - warp(src_v)) * valid_v [* expl_v]| with every gradient
-    produced by the same single pass (dvf_photo_loss_fused); backward only scales by the upstream scalar.
+    """sum over levels and views of mean|(tgt - warp(src_v)) * valid_v [* expl_v]| (dvf_photo_loss_fused_pose).
+
+    The kernel produces the loss and every gradient in ONE pass.  Two schedules, chosen per call:
+      * no gradients to the maps (image losses): the single pass runs in forward() for upstream gradient 1; backward()
+        multiplies the (small) depth / pose / mask gradients by the upstream scalar, out of place, so it can be
+        called again (retain_graph=True);
+      * gradients to the maps (feature losses): forward() runs the kernel forward-only, backward() runs the fused pass
+        with the upstream scalar handed over as a device pointer -- scaling three full feature-map gradients after
+        the fact costs more HBM traffic than re-reading the inputs (C4 shape: 110 us of scaling vs a ~60 us forward).
 
     inputs: cfg, pose [B,V,6], K, Kinv, then L target levels, L*V source levels (level-major),
             L depth levels [B,h,w], and L explainability levels [B,>=V,h,w] if cfg.has_expl.
@@ -340,102 +502,35 @@ class FusedPhotoLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, pose, K, Kinv, *tensors):
-        lib = _lib.load()
-        V, L = cfg.V, cfg.L
-        pose = _req(pose, "pose", 3)
-        K, Kinv = _req(K, "intrinsics", 3), _req(Kinv, "intrinsics_inv", 3)
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             raise DvfError("gradients w.r.t. the camera intrinsics are not implemented (unused by the reference)")
-        maps, layout, dtype = _req_maps(list(tensors[0:L + L * V]), "tgt/src")
-        tgts, srcs = maps[0:L], maps[L:L + L * V]
-        in_dtypes = [t.dtype for t in tensors[0:L + L * V]]
-        depths = [_req(t, "depth", 3) for t in tensors[L + L * V:2 * L + L * V]]
-        expls = [_req(t, "explainability_mask", 4) for t in tensors[2 * L + L * V:]] if cfg.has_expl else []
-        off = 4  # index of the first *tensors entry in needs_input_grad
-        need_tgt = [ctx.needs_input_grad[off + i] for i in range(L)]
-        need_src = [ctx.needs_input_grad[off + L + i] for i in range(L * V)]
-        need_depth = [ctx.needs_input_grad[off + L + L * V + i] for i in range(L)]
-        need_expl = [ctx.needs_input_grad[off + 2 * L + L * V + i] for i in range(L)] if cfg.has_expl else [False] * L
-        need_pose = ctx.needs_input_grad[1]
-
-        B, Cc = tgts[0].shape[0], tgts[0].shape[1]
-        dev = pose.device
-        vec = pose.reshape(B * V, 6)
-        # the kernel derives P and K^-1_s from the pose itself and finishes with the pose backward (one launch);
-        # dP is only materialised for the pose gradient, inside the kernel's workspace
-        g_pose = torch.empty(B, V, 6, device=dev, dtype=torch.float32) if need_pose else None
-        ds_arr = (C.c_float * L)(*[float(x) for x in cfg.downscales])
-        pargs = dvf_pose_args(vec.data_ptr(), K.data_ptr(), Kinv.data_ptr(), ds_arr, ROTATION[cfg.rotation_mode], 0,
-                              _ptr(g_pose))
-        terms = torch.empty(L * V, device=dev, dtype=torch.float32)
-
-        levels = (dvf_level * L)()
-        grads = []  # order: tgt(L), src(L*V), depth(L), expl(L)
-        g_tgt, g_src, g_depth, g_expl = [None] * L, [None] * (L * V), [None] * L, [None] * L
-        for l in range(L):
-            lv = levels[l]
-            h, w = depths[l].shape[1], depths[l].shape[2]
-            if tgts[l].shape != (B, Cc, h, w):
-                raise AssertionError(f"level {l}: target {list(tgts[l].shape)} does not match depth {list(depths[l].shape)}")
-            lv.H, lv.W = h, w
-            lv.depth, lv.tgt = depths[l].data_ptr(), tgts[l].data_ptr()
-            for v in range(V):
-                s = srcs[l * V + v]
-                if s.shape != tgts[l].shape:
-                    raise AssertionError(f"level {l} view {v}: source {list(s.shape)} != target {list(tgts[l].shape)}")
-                lv.src[v] = s.data_ptr()
-                if need_src[l * V + v]:
-                    g_src[l * V + v] = torch.zeros_like(s, dtype=torch.float32)   # fp32, same memory format
-                    lv.gsrc[v] = g_src[l * V + v].data_ptr()
-            if cfg.has_expl:
-                e = expls[l]
-                if e.shape[0] != B or e.shape[1] < V or e.shape[2:] != (h, w):
-                    raise AssertionError(f"level {l}: explainability mask {list(e.shape)} does not match depth")
-                lv.expl, lv.expl_bstride = e.data_ptr(), e.shape[1] * h * w
-                if need_expl[l]:
-                    # dense [B,V,h,w]; channels >= V of a wider mask get zero gradient
-                    g_expl[l] = torch.empty(B, V, h, w, device=dev, dtype=torch.float32)
-                    lv.gexpl = g_expl[l].data_ptr()
-            if need_depth[l]:
-                g_depth[l] = torch.empty_like(depths[l])
-                lv.gdepth = g_depth[l].data_ptr()
-            if need_tgt[l]:
-                g_tgt[l] = torch.empty_like(tgts[l], dtype=torch.float32)
-                lv.gtgt = g_tgt[l].data_ptr()
-        d = dvf_loss_desc(B, Cc, V, L, dtype, layout, PADDING[cfg.padding_mode], 0)
-        nbytes = lib.dvf_photo_loss_workspace_bytes(C.byref(d), levels)
-        if nbytes == 0:
-            raise DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")
-        ws = workspace(nbytes, dev, ('loss', B, Cc, V, cfg.has_expl) + tuple(tuple(x.shape[1:]) for x in depths))
-        _lib.check(lib.dvf_photo_loss_fused_pose(C.byref(d), levels, C.byref(pargs), _ptr(terms), _ptr(ws), ws.numel(),
-                                                 _stream()), "dvf_photo_loss_fused_pose")
-        for l in range(L):
-            if cfg.has_expl and need_expl[l] and expls[l].shape[1] > V:
-                full = torch.zeros_like(expls[l])
-                full[:, :V] = g_expl[l]
-                g_expl[l] = full
-        # gradients of the maps go back in the dtype the caller handed in
-        g_tgt = [g if g is None or g.dtype == in_dtypes[i] else g.to(in_dtypes[i]) for i, g in enumerate(g_tgt)]
-        g_src = [g if g is None or g.dtype == in_dtypes[L + i] else g.to(in_dtypes[L + i]) for i, g in enumerate(g_src)]
-        ctx.unit_grads = [g_pose] + g_tgt + g_src + g_depth + (g_expl if cfg.has_expl else [])
+        call = _LossCall(cfg, pose, K, Kinv, tensors, ctx.needs_input_grad)
+        ctx.call, ctx.unit_grads = None, None
+        if call.any_grad and not call.any_map_grad:
+            terms, ctx.unit_grads = call.run(True)
+        else:
+            terms, _ = call.run(False)
+            if call.any_grad:
+                ctx.call = call
         loss = terms.sum()
         ctx.mark_non_differentiable(terms)
         return loss, terms
 
     @staticmethod
     def backward(ctx, g_loss, _g_terms):
-        grads = ctx.unit_grads
-        ctx.unit_grads = None
-        if grads is None:
-            raise RuntimeError("FusedPhotoLoss: backward called twice (gradients are produced by the forward pass)")
-        _scale_inplace(grads, g_loss)
+        if ctx.call is not None:
+            _, grads = ctx.call.run(True, upstream=g_loss)
+        else:
+            grads = _scaled(ctx.unit_grads, g_loss)
         return (None, grads[0], None, None) + tuple(grads[1:])
 
 
 def fused_photo_loss(tgt_levels, src_levels, depth_levels, pose, K, Kinv, expl_levels=None, downscales=None,
-                     rotation_mode="euler", padding_mode="zeros"):
+                     rotation_mode="euler", padding_mode="zeros", align_corners=None, global_batch=None, nan_check=False):
     """tgt_levels: L tensors [B,C,h,w]; src_levels: L lists of V tensors; depth_levels: L tensors [B,h,w];
-    pose [B,V,6]; expl_levels: None or L tensors [B,>=V,h,w].  Returns (loss, terms[L*V])."""
+    pose [B,V,6]; expl_levels: None or L tensors [B,>=V,h,w].  Returns (loss, terms[L*V]).
+    global_batch: size of the whole (sharded) batch when this call holds only B of its images (dvf_b200.dist);
+    nan_check: collect NaN terms in ops.nan_flags() (the reference asserts per view and scale, loss_functions_sfm.py:34)."""
     L = len(depth_levels)
     V = pose.shape[1]
     if V > _lib.DVF_MAX_VIEWS or L > _lib.DVF_MAX_LEVELS:
@@ -445,6 +540,7 @@ def fused_photo_loss(tgt_levels, src_levels, depth_levels, pose, K, Kinv, expl_l
     cfg.rotation_mode, cfg.padding_mode = rotation_mode, padding_mode
     cfg.downscales = [1.0] * L if downscales is None else [float(x) for x in downscales]
     cfg.has_expl = expl_levels is not None
+    cfg.align_corners, cfg.global_batch, cfg.nan_check = align_corners, global_batch, bool(nan_check)
     flat = list(tgt_levels) + [s for lvl in src_levels for s in lvl] + list(depth_levels)
     if cfg.has_expl:
         flat += list(expl_levels)
@@ -486,10 +582,7 @@ class RegLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out):
-        grads = ctx.unit_grads
-        ctx.unit_grads = None
-        _scale_inplace(grads, g_out)
-        return (None, None) + tuple(grads)
+        return (None, None) + tuple(_scaled(ctx.unit_grads, g_out))
 
 
 def smooth_loss(maps, scale_factor=1):

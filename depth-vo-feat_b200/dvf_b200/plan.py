@@ -23,7 +23,16 @@ class FusedLossPlan:
     def __init__(self, tgt_levels: Sequence[torch.Tensor], src_levels: Sequence[Sequence[torch.Tensor]],
                  depth_levels: Sequence[torch.Tensor], pose: torch.Tensor, K: torch.Tensor, Kinv: torch.Tensor,
                  expl_levels: Optional[Sequence[torch.Tensor]] = None, downscales: Optional[Sequence[float]] = None,
-                 rotation_mode: str = "euler", padding_mode: str = "zeros", need_grad: bool = True):
+                 rotation_mode: str = "euler", padding_mode: str = "zeros", need_grad: bool = True,
+                 map_grads: bool = False, global_batch: Optional[int] = None, align_corners: bool = False,
+                 upstream: Optional[torch.Tensor] = None, fused_pose: bool = True, use_tma: bool = True,
+                 piece_overhead: int = 0, ctas_per_sm: int = 0, pdl: bool = False):
+        """Maps: dense NCHW fp32 (images, any C) or channels-last fp32 / bf16 feature maps ([B,C,H,W] tensors in
+        torch.channels_last memory).  map_grads: also produce d/d tgt and d/d src (fp32, layout of the maps).
+        global_batch: this plan holds B of the global_batch images of a sharded batch (dvf_loss_desc.mean_batch).
+        upstream: device scalar multiplying every gradient (dvf_loss_desc.upstream).
+        pdl: programmatic dependent launch (DVF_FLAG_PDL): back-to-back launches of plans with DISJOINT buffers overlap."""
+        from .ops import _nhwc_ok
         self.lib = _lib.load()
         dev = pose.device
         L, V = len(depth_levels), pose.shape[1]
@@ -31,9 +40,18 @@ class FusedLossPlan:
         self.B, self.C, self.V, self.L = B, Cc, V, L
         self.rotation = ROTATION[rotation_mode]
         self.inputs = (list(tgt_levels), [list(s) for s in src_levels], list(depth_levels), pose, K, Kinv,
-                       None if expl_levels is None else list(expl_levels))   # keep alive
-        for t in list(tgt_levels) + [s for lv in src_levels for s in lv] + list(depth_levels) + [pose, K, Kinv]:
+                       None if expl_levels is None else list(expl_levels), upstream)   # keep alive
+        maps = list(tgt_levels) + [s for lv in src_levels for s in lv]
+        if all(_nhwc_ok(t) for t in maps) and len({t.dtype for t in maps}) == 1:
+            layout, dtype = _lib.NHWC, (_lib.BF16 if maps[0].dtype == torch.bfloat16 else _lib.F32)
+        else:
+            layout, dtype = _lib.NCHW, _lib.F32
+            for t in maps:
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        for t in list(depth_levels) + [pose, K, Kinv] + ([] if expl_levels is None else list(expl_levels)):
             assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        self.layout, self.dtype = layout, dtype
+        self.elem_bytes = 2 if dtype == _lib.BF16 else 4
         ds = [1.0] * L if downscales is None else [float(x) for x in downscales]
         self.ds = (C.c_float * L)(*ds)
         self.P = torch.empty(L, B * V, 3, 4, device=dev)
@@ -44,6 +62,10 @@ class FusedLossPlan:
         self.gdepth = [torch.empty_like(d) for d in depth_levels] if need_grad else None
         self.gexpl = ([torch.empty(B, V, e.shape[2], e.shape[3], device=dev) for e in expl_levels]
                       if (need_grad and expl_levels is not None) else None)
+        self.map_grads = bool(map_grads and need_grad)
+        self.gtgt = [torch.empty_like(t, dtype=torch.float32) for t in tgt_levels] if self.map_grads else None
+        self.gsrc = ([[torch.empty_like(t, dtype=torch.float32) for t in lv] for lv in src_levels]
+                     if self.map_grads else None)   # zero-filled by the entry on every launch (DVF_FLAG_ZERO_GSRC)
         self.levels = (dvf_level * L)()
         for l in range(L):
             lv = self.levels[l]
@@ -59,7 +81,14 @@ class FusedLossPlan:
                 lv.gdepth, lv.gP = self.gdepth[l].data_ptr(), self.gP[l].data_ptr()
                 if self.gexpl is not None:
                     lv.gexpl = self.gexpl[l].data_ptr()
-        self.desc = dvf_loss_desc(B, Cc, V, L, _lib.F32, _lib.NCHW, PADDING[padding_mode], 0)
+                if self.map_grads:
+                    lv.gtgt = self.gtgt[l].data_ptr()
+                    for v in range(V):
+                        lv.gsrc[v] = self.gsrc[l][v].data_ptr()
+        flags = (_lib.FLAG_ALIGN_CORNERS if align_corners else 0) | (_lib.FLAG_ZERO_GSRC if self.map_grads else 0) | \
+                (0 if use_tma else _lib.FLAG_NO_TMA) | (_lib.FLAG_PDL if pdl else 0)
+        self.desc = dvf_loss_desc(B, Cc, V, L, dtype, layout, PADDING[padding_mode], flags, int(global_batch or 0), _lib.F32,
+                                  int(piece_overhead), int(ctas_per_sm), None if upstream is None else upstream.data_ptr(), None)
         n = self.lib.dvf_photo_loss_workspace_bytes(C.byref(self.desc), self.levels)
         if n == 0:
             raise _lib.DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")
@@ -69,8 +98,7 @@ class FusedLossPlan:
         # single-launch form: pose -> P in the kernel prologue, d pose in its epilogue
         self.pose_args = dvf_pose_args(pose.data_ptr(), K.data_ptr(), Kinv.data_ptr(), self.ds, self.rotation, 0,
                                        self.gpose.data_ptr() if need_grad else None)
-        import os
-        self.fused_pose = os.environ.get("DVF_PLAN_FUSED_POSE", "1") != "0"   # 0: three-launch form (debug / A-B timing)
+        self.fused_pose = bool(fused_pose)   # False: three-launch form (debug / A-B timing)
         self.n_launches = 1 if self.fused_pose else (3 if need_grad else 2)
 
     # -- the three launches ---------------------------------------------------------------------
@@ -123,10 +151,14 @@ class FusedLossPlan:
 
     # -- algorithmic (compulsory) HBM bytes of one fused-loss launch, SURVEY 8(d) ------------------
     def algorithmic_bytes(self) -> int:
-        e = 4
-        per_tpx = 4 + self.C * e + (4 if self.need_grad else 0)          # depth + target (+ d depth), once per target pixel
+        e = self.elem_bytes
+        g = 4 if self.need_grad else 0
+        per_tpx = 4 + self.C * e + g                                      # depth + target (+ d depth), once per target pixel
         per_wpx = self.C * e                                              # source texels, once per warped pixel
+        if self.map_grads:
+            per_tpx += self.C * 4                                         # d target (fp32), written once
+            per_wpx += self.C * 4                                         # d source (fp32), one write per texel
         if self.inputs[6] is not None:
-            per_wpx += 4 + (4 if self.need_grad else 0)                   # explainability read (+ its gradient)
+            per_wpx += 4 + g                                              # explainability read (+ its gradient)
         tpx = self.warped_px // self.V
         return tpx * per_tpx + self.warped_px * per_wpx

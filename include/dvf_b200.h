@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DVF_ABI_VERSION 1
+#define DVF_ABI_VERSION 2
 #define DVF_MAX_VIEWS 4   /* source views per target in one loss call          */
 #define DVF_MAX_LEVELS 6  /* pyramid levels fused into one loss launch         */
 
@@ -56,13 +56,38 @@ typedef enum dvf_layout { DVF_NCHW = 0, DVF_NHWC = 1 } dvf_layout;
 typedef enum dvf_padding { DVF_PAD_ZEROS = 0, DVF_PAD_BORDER = 1 } dvf_padding;   /* inverse_warp.py:67, train.py:194 */
 typedef enum dvf_rotation { DVF_ROT_EULER = 0, DVF_ROT_QUAT = 1 } dvf_rotation;  /* inverse_warp.py:152-155 */
 
+/* Descriptor flags (dvf_desc.flags, dvf_loss_desc.flags); no environment variables are read anywhere. */
+typedef enum dvf_flags {
+  /* F.grid_sample(align_corners=True): ix = (x+1)/2*(W-1).  The reference never passes align_corners
+   * (inverse_warp.py:191): torch <= 1.2, which it was written for, sampled this way; torch >= 1.3
+   * defaults to False, which is this library's default (flag clear).                               */
+  DVF_FLAG_ALIGN_CORNERS = 1,
+  /* loss entries: gsrc maps are zero-filled by the entry (cudaMemsetAsync on the caller's stream)
+   * before the launch instead of by the caller                                                    */
+  DVF_FLAG_ZERO_GSRC = 2,
+  /* loss entries: in-kernel replacement of the reference's per-(scale, view) NaN assertion
+   * (loss_functions_sfm.py:34, one device synchronisation each): bit l*V+v of *nan_flags is set
+   * when terms[l*V+v] is NaN; the caller reads the word whenever it likes                        */
+  DVF_FLAG_NAN_CHECK = 4,
+  /* loss entries: plain loads instead of the bulk-copy (TMA) ring of the image kernel (A/B timing) */
+  DVF_FLAG_NO_TMA = 8,
+  /* loss entries (image and channels-last kernels): programmatic dependent launch.  The launch carries the
+   * programmatic-stream-serialisation attribute and lets its successor start early in turn, so that back-to-back
+   * loss launches (micro-batches, the views of a step, consecutive steps of a captured graph) overlap the serial
+   * tail of one launch (ticket, fp64 fold, pose backward) and the launch gap with the pixel work of the next.
+   * The kernel waits for the PREVIOUS kernel of the stream to complete before its first workspace access, but it
+   * reads its inputs and writes its gradient outputs before that.  CONTRACT: the previous kernel in the stream
+   * neither writes an input of this launch nor touches one of its outputs.                                   */
+  DVF_FLAG_PDL = 16
+} dvf_flags;
+
 /* Image-tensor descriptor shared by the warp and loss entries. */
 typedef struct dvf_desc {
   int32_t B, C, H, W;
   int32_t dtype;    /* dvf_dtype of img / warped / gout / gimg / tgt / src    */
   int32_t layout;   /* dvf_layout of those tensors                            */
   int32_t padding;  /* dvf_padding                                            */
-  int32_t reserved;
+  int32_t flags;    /* dvf_flags (DVF_FLAG_ALIGN_CORNERS)                     */
 } dvf_desc;
 
 int dvf_version(void);
@@ -137,15 +162,24 @@ typedef struct dvf_level {
   const float* Kinv;                /* [B,3,3]                                */
   float* gdepth;                    /* [B,H,W] written                        */
   float* gexpl;                     /* [B,V,H,W] dense, written               */
-  void* gsrc[DVF_MAX_VIEWS];        /* fp32, layout of src; ACCUMULATED       */
-  void* gtgt;                       /* fp32, layout of tgt; written           */
+  void* gsrc[DVF_MAX_VIEWS];        /* grad_dtype, layout of src; ACCUMULATED (see DVF_FLAG_ZERO_GSRC) */
+  void* gtgt;                       /* grad_dtype, layout of tgt; written     */
   float* gP;                        /* [B,V,3,4] written                      */
 } dvf_level;
 
 typedef struct dvf_loss_desc {
   int32_t B, C, V, n_levels;
   int32_t dtype, layout, padding;
-  int32_t reserved;
+  int32_t flags;          /* dvf_flags                                                              */
+  int32_t mean_batch;     /* batch size in the denominator of the means; 0 = B.  A rank that holds B
+                             of the mean_batch images of a sharded batch passes the global size and
+                             gets its share of the global loss and gradients (no collective needed) */
+  int32_t grad_dtype;     /* dvf_dtype of gsrc / gtgt: DVF_F32, or DVF_BF16 for NHWC bf16 maps      */
+  int32_t piece_overhead; /* tuning: fixed cost of an (image, level) piece in 256-px units; <= 0 = default */
+  int32_t ctas_per_sm;    /* tuning: resident CTAs per SM of the image kernel's grid; <= 0 = occupancy query */
+  const float* upstream;  /* device scalar g = d(total)/d(sum of terms): every gradient is scaled by it
+                             (terms are not); NULL = 1                                              */
+  int32_t* nan_flags;     /* device word for DVF_FLAG_NAN_CHECK, OR-ed into (never cleared); nullable */
 } dvf_loss_desc;
 
 size_t dvf_photo_loss_workspace_bytes(const dvf_loss_desc* d, const dvf_level* levels);

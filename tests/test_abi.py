@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_version_and_strerror(lib):
-    assert lib.dvf_version() == 1
+    assert lib.dvf_version() == 2
     assert lib.dvf_strerror(0) == b"ok"
     assert b"workspace" in lib.dvf_strerror(-6)
     assert b"unknown" in lib.dvf_strerror(-99)
