@@ -300,3 +300,4 @@ DVF_EXPORT int dvf_photo_loss_fused_pose(const dvf_loss_desc* d, const dvf_level
   if (!pose) return DVF_EINVAL_NULL;
   return run_loss(d, levels, pose, terms, workspace, workspace_bytes, stream);
 }
+

@@ -30,6 +30,20 @@ namespace dvf {
 
 constexpr int kLossThreads = 128;
 
+#ifdef DVF_TRACE   // experiment builds: per-CTA timestamps of the first piece (profiles/trace_pieces.py)
+static __device__ unsigned long long g_trace[8192 * 8];   // one copy per translation unit
+__device__ __forceinline__ void trace_mark(int slot) {
+  if (threadIdx.x == 0 && blockIdx.x < 8192) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[blockIdx.x * 8 + slot] = t;
+  }
+}
+#define DVF_MARK(slot) trace_mark(slot)
+#else
+#define DVF_MARK(slot)
+#endif
+
 struct LevelDev {
   int H, W, HW;
   FastDiv divW;
@@ -74,6 +88,12 @@ struct LossParams {
   int ctas_per_sm;         // > 0: grid override of the balanced kernels (tuning)
   int grad_bf16;           // NHWC bf16 maps: map gradients are bf16
   int pdl;                 // programmatic dependent launch (DVF_FLAG_PDL)
+  // balanced split in 32-bit arithmetic (set by launch_balanced once the grid G is known): CTA c owns units
+  // [c*q + floor(c*r/G), ...) with T = q*G + r -- the same values as floor(c*T/G) without 64-bit divisions, which cost
+  // ~1 us per piece when every issue slot of the SM is contended (profiles/trace_pieces.py)
+  int split_q, split_r, grid;
+  float ctas_per_unit;     // G / T
+  FastDiv div_grid, div_upi;   // division by G and by units_per_image_all
   const float* upstream;   // device scalar multiplying every gradient, or nullptr (= 1)
   int* nan_flags;          // nullptr, or a word that collects bit l*V+v when term (l, v) is NaN
   // pose mode (dvf_photo_loss_fused_pose): P / K^-1_s are derived in the CTA prologue, d pose in the epilogue
@@ -131,32 +151,38 @@ static __device__ __noinline__ float euler_angle_grad(const double* gM /*3x4*/, 
 // CTA prologue: projection matrices of image b at this level into shared memory -- either read from the
 // arrays the caller computed (dvf_pose_proj_fwd) or derived here from the 6-DoF vectors (same routines).
 template <int kV>
-__device__ __forceinline__ void load_matrices(const LossParams& prm, const LevelDev& lv, int b, float (*s_P)[12], float* s_M) {
+__device__ __forceinline__ void load_matrices(const LossParams& prm, const LevelDev& lv, int b, float (*s_P)[12], float* s_M,
+                                              bool new_image = true) {
   const int tid = threadIdx.x;
   if (prm.pose_vec) {
     // Three short stages, each spread over threads so that the prologue costs one global-load latency plus a
-    // few hundred cycles: (1) fetch vec / K / K^-1, (2) sin / cos (torch-CPU order, dvf_pose.cuh) and the level's scaled intrinsics,
-    // (3) every thread of the first kV*12 composes R and takes one entry of P = K_s @ [R|t].
-    // Operation order per entry is identical to dvf_pose_proj_fwd.
+    // few hundred cycles: (1) fetch vec / K / K^-1, (2) sin / cos (torch-CPU order, dvf_pose.cuh) and the level's scaled
+    // intrinsics, (3) every thread of the first kV*12 composes R and takes one entry of P = K_s @ [R|t].
+    // Operation order per entry is identical to dvf_pose_proj_fwd.  new_image = false (CTA-uniform): the previous piece
+    // of this CTA belonged to the same image, so vec, sin / cos, K and K^-1 are still in shared memory and only the
+    // level-dependent part is redone (no global load, no trigonometry: the pieces of the small pyramid levels).
     __shared__ float s_vec[kV][6];
     __shared__ float s_trig[kV][6];
+    __shared__ float s_K0[9], s_Ki0[9];
     __shared__ float s_Ks[9];
     const bool euler = prm.rotation == DVF_ROT_EULER;
-    if (tid < kV * 6) s_vec[tid / 6][tid % 6] = prm.pose_vec[((size_t)b * kV + tid / 6) * 6 + tid % 6];
-    else if (tid >= 32 && tid < 41) s_Ks[tid - 32] = prm.K[b * 9 + (tid - 32)];
-    else if (tid >= 64 && tid < 73) s_M[tid - 64] = prm.Kinv[b * 9 + (tid - 64)];
-    __syncthreads();
+    if (new_image) {
+      if (tid < kV * 6) s_vec[tid / 6][tid % 6] = prm.pose_vec[((size_t)b * kV + tid / 6) * 6 + tid % 6];
+      else if (tid >= 32 && tid < 41) s_K0[tid - 32] = prm.K[b * 9 + (tid - 32)];
+      else if (tid >= 64 && tid < 73) s_Ki0[tid - 64] = prm.Kinv[b * 9 + (tid - 64)];
+      __syncthreads();
+    }
     if (tid < kV * 6) {
-      if (euler) {
+      if (euler && new_image) {
         const int v = tid / 6, q = tid % 6;           // q: 0 cz, 1 sz, 2 cy, 3 sy, 4 cx, 5 sx
         s_trig[v][q] = trig_of(s_vec[v][3 + (2 - q / 2)], q & 1);
       }
     } else if (tid >= 32 && tid < 41) {
       const int q = tid - 32;
-      if (q < 6 && lv.ds != 1.0f) s_Ks[q] = div(s_Ks[q], lv.ds);               // rows 0-1 / downscale
+      s_Ks[q] = (q < 6 && lv.ds != 1.0f) ? div(s_K0[q], lv.ds) : s_K0[q];               // rows 0-1 / downscale
     } else if (tid >= 64 && tid < 73) {
       const int q = tid - 64;
-      if ((q % 3) < 2 && lv.ds != 1.0f) s_M[q] = mul(s_M[q], lv.ds);          // columns 0-1 * downscale
+      s_M[q] = ((q % 3) < 2 && lv.ds != 1.0f) ? mul(s_Ki0[q], lv.ds) : s_Ki0[q];         // columns 0-1 * downscale
     }
     __syncthreads();
     if (tid < kV * 12) {
@@ -176,17 +202,17 @@ __device__ __forceinline__ void load_matrices(const LossParams& prm, const Level
 }
 
 // Programmatic dependent launch (DVF_FLAG_PDL): every CTA lets the NEXT kernel of the stream be scheduled as soon as
-// SM slots free up, and waits for the PREVIOUS kernel to have completed (memory flushed) before it first touches the
-// workspace -- partial sums and ticket counters may be shared with it.  Inputs are read and gradient maps written
-// before that (contract in include/dvf_b200.h).  Both instructions are no-ops in a launch without the attribute.
+// SM slots free up, and runs WITHOUT waiting for the previous kernel: by contract (include/dvf_b200.h) that kernel
+// shares no buffer with this launch, workspace included.  A CTA only waits for it right before it exits, so that
+// kernels still complete in stream order (whoever waits for this grid has then waited for its predecessors too);
+// by then the predecessor is long done.  A first version waited before the first workspace access instead (shared
+// workspaces allowed): CTAs that had started early on freed SM slots then idled for up to 40 us (median 5 us) holding
+// their slots -- profiles/trace_pieces.py.  Both instructions are no-ops in a launch without the attribute.
 __device__ __forceinline__ void pdl_let_successor_start(const LossParams& prm) {
   if (prm.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-__device__ __forceinline__ void pdl_wait_predecessor(const LossParams& prm, bool& done) {
-  if (prm.pdl && !done) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    done = true;
-  }
+__device__ __forceinline__ void pdl_wait_predecessor(const LossParams& prm) {
+  if (prm.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // sign(d)/N with sign(0) = sign(NaN) = 0, gated by `gate`
@@ -212,31 +238,55 @@ __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], c
     if ((lane & 1) == 0) s_red[warp][v][butterfly_slot(lane)] = r;
   }
   __syncthreads();
-  float* const img_part = lv.partials + (size_t)b * lv.slots_per_image * kV * kRedSlots;
-  float* const my_part = img_part + (size_t)part * kV * kRedSlots;
-  if (tid < kV * kRedSlots) {
-    const int v = tid / kRedSlots, s = tid % kRedSlots;
-    float t = 0.0f;
+  if (n_parts == 1) {
+    // the whole (image, level) was this CTA's: its sums are final -- no partials in global memory, no ticket
+    if (tid < kV * kRedSlots) {
+      const int v = tid / kRedSlots, sl = tid % kRedSlots;
+      float t = 0.0f;
 #pragma unroll
-    for (int w8 = 0; w8 < kThreadsT / 32; ++w8) t += s_red[w8][v][s];
-    __stcg(my_part + tid, t);
-    __threadfence();   // only the writers need to publish
+      for (int w8 = 0; w8 < kThreadsT / 32; ++w8) t += s_red[w8][v][sl];
+      const double sum = (double)t;   // same value as the fp64 fold of a single partial
+      if (sl < 12) {
+        if (lv.gP) lv.gP[((size_t)b * kV + v) * 12 + sl] = (float)sum;
+        s_gp[v][sl] = (float)sum;
+      } else if (sl == 12) {
+        lv.img_terms[(size_t)b * kV + v] = sum;
+      }
+    }
+    if (tid == 0) s_flag = 1;
+  } else {
+    float* const img_part = lv.partials + (size_t)b * lv.slots_per_image * kV * kRedSlots;
+    float* const my_part = img_part + (size_t)part * kV * kRedSlots;
+    if (tid < kV * kRedSlots) {
+      const int v = tid / kRedSlots, sl = tid % kRedSlots;
+      float t = 0.0f;
+#pragma unroll
+      for (int w8 = 0; w8 < kThreadsT / 32; ++w8) t += s_red[w8][v][sl];
+      __stcg(my_part + tid, t);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();   // cumulative: publishes the partial stores of the whole CTA (ordered before it by the barrier)
+      s_flag = (atomicAdd(lv.img_counter + b, 1u) == (unsigned)(n_parts - 1));
+      if (s_flag) lv.img_counter[b] = 0u;   // last arrival: restore the counter for the next launch
+    }
   }
   __syncthreads();
-  if (tid == 0) s_flag = (atomicAdd(lv.img_counter + b, 1u) == (unsigned)(n_parts - 1));
-  __syncthreads();
   if (s_flag) {   // CTA-uniform
-    // ---- last piece of image b: fixed-order fp64 fold of the partials ----------------
-    __threadfence();
-    for (int pair = tid >> 3; pair < kV * kRedSlots; pair += kThreadsT / 8) {
-      const int v = pair / kRedSlots, s = pair % kRedSlots;
-      const double sum = group8_sum(img_part + v * kRedSlots + s, n_parts, kV * kRedSlots, tid & 7);
-      if ((tid & 7) == 0) {
-        if (s < 12) {
-          if (lv.gP) lv.gP[((size_t)b * kV + v) * 12 + s] = (float)sum;
-          s_gp[v][s] = (float)sum;
-        } else if (s == 12) {
-          lv.img_terms[(size_t)b * kV + v] = sum;
+    if (n_parts > 1) {
+      // ---- last piece of image b: fixed-order fp64 fold of the partials ----------------
+      float* const img_part = lv.partials + (size_t)b * lv.slots_per_image * kV * kRedSlots;
+      __threadfence();
+      for (int pair = tid >> 3; pair < kV * kRedSlots; pair += kThreadsT / 8) {
+        const int v = pair / kRedSlots, sl = pair % kRedSlots;
+        const double sum = group8_sum(img_part + v * kRedSlots + sl, n_parts, kV * kRedSlots, tid & 7);
+        if ((tid & 7) == 0) {
+          if (sl < 12) {
+            if (lv.gP) lv.gP[((size_t)b * kV + v) * 12 + sl] = (float)sum;
+            s_gp[v][sl] = (float)sum;
+          } else if (sl == 12) {
+            lv.img_terms[(size_t)b * kV + v] = sum;
+          }
         }
       }
     }
@@ -288,10 +338,7 @@ __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], c
       }
       __syncthreads();
     }
-    if (tid == 0) {
-      lv.img_counter[b] = 0u;
-      s_flag = (atomicAdd(lv.lvl_counter, 1u) == (unsigned)(prm.B - 1));
-    }
+    if (tid == 0) s_flag = (atomicAdd(lv.lvl_counter, 1u) == (unsigned)(prm.B - 1));
     __syncthreads();
     if (s_flag) {
       // ---- last image of the level: loss terms ---------------------------------------------
@@ -336,9 +383,18 @@ constexpr int kPlanUnit = 512;   // granularity (pixels) of the host's work spli
 constexpr int kUnitPx = 2 * kLossThreads;   // image kernel: one unit = one pixel pair per thread of the CTA
 constexpr int kStages = 4;
 
-// CTA that owns global unit g when CTA c owns [floor(c*T/G), floor((c+1)*T/G))
-__device__ __forceinline__ int cta_of_unit(int g, int G, int T) {
-  return (int)((((long long)g + 1) * G - 1) / T);
+// first unit of CTA c (c in [0, G]) = floor(c*T/G)
+__device__ __forceinline__ int split_start(int c, const LossParams& prm) {
+  return c * prm.split_q + (int)fastdiv((uint32_t)c * (uint32_t)prm.split_r, prm.div_grid);   // c*r < G*G < 2^31
+}
+// CTA that owns global unit g when CTA c owns [floor(c*T/G), floor((c+1)*T/G)): float estimate (exact to well below
+// one CTA: g < 2^31, G <= 2^13), then fixed up against the exact integer bounds
+__device__ __forceinline__ int cta_of_unit(int g, const LossParams& prm) {
+  int c = (int)(((float)g + 0.5f) * prm.ctas_per_unit);
+  c = min(max(c, 0), prm.grid - 1);
+  while (c > 0 && split_start(c, prm) > g) --c;
+  while (c + 1 < prm.grid && split_start(c + 1, prm) <= g) ++c;
+  return c;
 }
 
 // Resident CTAs per SM the register allocation is sized for.  One or two views: 4 (128 registers; 5 CTAs = 96 registers
@@ -352,6 +408,11 @@ constexpr int c3_min_blocks(int views) { return views >= 3 ? 3 : 4; }
 template <int kV, bool kZeros, bool kExpl, bool kGrad, bool kTma, int kMinBlocks = c3_min_blocks(kV)>
 __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kernel(const __grid_constant__ LossParams prm) {
   constexpr int kC = 3;
+#ifdef DVF_ACC_SMEM
+  constexpr bool kAccSmem = kV == 1;
+#else
+  constexpr bool kAccSmem = false;
+#endif
   constexpr int kPlanes = 1 + kC + (kExpl ? kV : 0);   // streamed planes per chunk
   // pixel pairs per thread between two ring hand-overs (= CTA barriers).  Measured on C2 with the balanced split:
   // 2 pairs x 4 stages 69.6 us, 3 x 3 69.4 us, 4 x 2 67.5 us; with masks the stages get too large for more than 1.
@@ -362,7 +423,11 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
 #endif
   constexpr int kChunk = kUnitPx * kPairsPerChunk;    // pixels per chunk
   // ring depth: as deep as 40 KB of static shared memory allow (4 CTAs per SM stay resident), at least 2
+#ifdef DVF_RING_BYTES
+  constexpr int kStagesFit = DVF_RING_BYTES / (kPlanes * kChunk * 4);
+#else
   constexpr int kStagesFit = 40000 / (kPlanes * kChunk * 4);
+#endif
   constexpr int kSt = kStagesFit >= kStages ? kStages : (kStagesFit < 2 ? 2 : kStagesFit);
   __shared__ __align__(16) float s_P[kV][12];
   __shared__ __align__(16) float s_M[12];
@@ -378,15 +443,16 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
 
   // balanced split: this CTA owns units [w, w_end) of the launch-wide unit list; it walks them (image, level) by
   // (image, level) -- "pieces", each with its own matrices, accumulators and partial-sum slot
-  const int G = (int)gridDim.x, T = prm.total_units;
-  int w = (int)((long long)blockIdx.x * T / G);
-  const int w_end = (int)(((long long)blockIdx.x + 1) * T / G);
+  int w = split_start((int)blockIdx.x, prm);
+  const int w_end = split_start((int)blockIdx.x + 1, prm);
   int ring_k = 0;   // chunks this CTA has pushed through the ring so far (stage / parity bookkeeping)
   pdl_let_successor_start(prm);
-  bool pdl_waited = false;
+  DVF_MARK(0);
+  int piece_no = 0;
+  int prev_b = -1;   // image whose pose / intrinsics sit in shared memory
 
   while (w < w_end) {
-  const int b = w / prm.units_per_image_all;
+  const int b = (int)fastdiv((uint32_t)w, prm.div_upi);
   int l = 0;
   while (l + 1 < prm.n_levels && w - b * prm.units_per_image_all >= prm.lv[l + 1].unit_base) ++l;
   const LevelDev& lv = prm.lv[l];
@@ -394,10 +460,13 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   const int real1 = real0 + lv.units_per_image;
   const int piece_end = min(w_end, real1);
   const int k0 = max(w, real0) - real0, k1 = piece_end - real0;   // units [k0, k1) of image b at level l
+  const bool piece_starts_here = w <= real0, piece_ends_here = piece_end == real1;
   w = piece_end;
   if (k1 <= k0) continue;   // only overhead units fell into my range (CTA-uniform)
-  const int first_cta = cta_of_unit(real0, G, T);
-  const int n_parts = cta_of_unit(real1 - 1, G, T) - first_cta + 1;
+  // which of the CTA pieces of (b, l) this is: only pieces that are cut by a CTA boundary need the search
+  const int first_cta = piece_starts_here ? (int)blockIdx.x : cta_of_unit(real0, prm);
+  const int last_cta = piece_ends_here ? (int)blockIdx.x : cta_of_unit(real1 - 1, prm);
+  const int n_parts = last_cta - first_cta + 1;
   const int part = (int)blockIdx.x - first_cta;
   const int H = lv.H, W = lv.W, HW = lv.HW;
   const Geo geo = lv.geo;
@@ -405,14 +474,20 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   const FastDiv divW = lv.divW;
   const float inv_n = prm.upstream ? mul(lv.inv_n, __ldg(prm.upstream)) : lv.inv_n;
 
-  f2 acc2[kV][12];     // dL/dP partial sums, (A,B) lanes folded at the end
+  // dL/dP partial sums, (A,B) lanes folded at the end.  kAccSmem: they live in thread-private shared memory
+  // (column tid of s_acc) instead of 24 registers
+  __shared__ f2 s_acc[kAccSmem ? 12 : 1][kAccSmem ? kLossThreads : 1];
+  f2 acc2[kV][12];
+#pragma unroll
+  for (int v = 0; v < kV; ++v)
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      if (kAccSmem) s_acc[k][tid] = dup(0.0f);
+      else acc2[v][k] = dup(0.0f);
+    }
   float accl[kV];      // loss partial sums
 #pragma unroll
-  for (int v = 0; v < kV; ++v) {
-#pragma unroll
-    for (int k = 0; k < 12; ++k) acc2[v][k] = dup(0.0f);
-    accl[v] = 0.0f;
-  }
+  for (int v = 0; v < kV; ++v) accl[v] = 0.0f;
 
   const float* const depth_b = lv.depth + (size_t)b * HW;
   const float* const tgt0 = lv.tgt + (size_t)b * kC * HW;
@@ -461,8 +536,11 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   }
 
   // projection matrices of this image (overlaps with the bulk copies just issued)
-  load_matrices<kV>(prm, lv, b, s_P, s_M);
+  if (piece_no == 0) DVF_MARK(1);
+  load_matrices<kV>(prm, lv, b, s_P, s_M, b != prev_b);
+  prev_b = b;
   __syncthreads();
+  if (piece_no == 0) DVF_MARK(2);
   bool mats_ok = lv.allow_fast != 0;
   float M[9];
 #pragma unroll
@@ -533,7 +611,14 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
       const int ca = kTail ? min(idxA, HW - 1) : idxA, cb = kTail ? min(idxB, HW - 1) : idxB;
       const int iA = (int)fastdiv((uint32_t)ca, divW), jA = ca - iA * W;
       const int iB = (int)fastdiv((uint32_t)cb, divW), jB = cb - iB * W;
+#ifdef DVF_M_SMEM
+      float Mv[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) Mv[q] = *reinterpret_cast<volatile float*>(&s_M[q]);
+      pixel_to_cam2(Mv, dep, make_float2((float)iA, (float)iB), make_float2((float)jA, (float)jB), cam);
+#else
       pixel_to_cam2(M, dep, make_float2((float)iA, (float)iB), make_float2((float)jA, (float)jB), cam);
+#endif
     }
     const bool fastA = fabsf(dep.x) <= depth_max, fastB = fabsf(dep.y) <= depth_max;   // false for NaN
     const bool slow = !(fastA && fastB);
@@ -664,6 +749,12 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
         gd = make_float2(add(gd.x, cg.gdepth.x), add(gd.y, cg.gdepth.y));
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
+          if (kAccSmem) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) s_acc[r * 4 + q][tid] = fma2(cg.gq[r], cam.cam[q], s_acc[r * 4 + q][tid]);
+            s_acc[r * 4 + 3][tid] = add2(s_acc[r * 4 + 3][tid], cg.gq[r]);
+            continue;
+          }
 #pragma unroll
           // With several views the (A,B) halves are folded right away: 12 instead of 24 accumulator registers per
           // view (two scalar FMAs occupy the FMA pipe as long as one packed one).  Measured on C2: V=2 spills 276 B ->
@@ -692,6 +783,7 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
       if (tid == 0 && k + kSt < n_chunks) issue(k + kSt);
     }
   };
+  if (kTma && piece_no == 0) { mbar_wait(&s_full[ring_k % kSt], (uint32_t)(ring_k / kSt) & 1u); DVF_MARK(3); }
   for (int k = 0; k + 1 < n_chunks; ++k) do_chunk(k, std::false_type{});
   if (n_chunks > 0) {
     if ((px_end - px_begin) % kUnitPx == 0) do_chunk(n_chunks - 1, std::false_type{});
@@ -703,13 +795,22 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
 #pragma unroll
   for (int v = 0; v < kV; ++v) {
 #pragma unroll
-    for (int q = 0; q < 12; ++q) acc[v][q] = acc2[v][q].x + acc2[v][q].y;
+    for (int q = 0; q < 12; ++q) acc[v][q] = kAccSmem ? s_acc[q][tid].x + s_acc[q][tid].y : acc2[v][q].x + acc2[v][q].y;
     acc[v][12] = accl[v];
     acc[v][13] = acc[v][14] = acc[v][15] = 0.0f;
   }
-  pdl_wait_predecessor(prm, pdl_waited);
+  if (piece_no == 0) DVF_MARK(4);
+  if (piece_no == 0) DVF_MARK(5);
   reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, part, n_parts, b, kC);
+  if (piece_no == 0) {
+    DVF_MARK(6);
+#ifdef DVF_TRACE
+    if (tid == 0 && blockIdx.x < 8192) g_trace[blockIdx.x * 8 + 7] = (unsigned long long)(px_end - px_begin);
+#endif
+  }
+  ++piece_no;
   }  // pieces of this CTA
+  pdl_wait_predecessor(prm);
 }
 
 // ================================================================================================
@@ -855,7 +956,8 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_cn_kernel(const __
 // Launch of the image kernel: one CTA per resident slot of this variant (occupancy query, cached per variant), every
 // CTA an equal share of the units => a single wave without a tail.  dvf_loss_desc.ctas_per_sm overrides (tuning aid).
 template <void (*kKernel)(const LossParams)>
-inline void launch_balanced(const LossParams& prm, int cap, cudaStream_t st) {
+inline void launch_balanced(const LossParams& prm_in, int cap, cudaStream_t st) {
+  LossParams prm = prm_in;
   static int per_sm = 0;   // benign race: every thread computes the same value
   if (per_sm == 0) {
     int n = 0;
@@ -865,6 +967,12 @@ inline void launch_balanced(const LossParams& prm, int cap, cudaStream_t st) {
   long long g = (long long)(prm.ctas_per_sm > 0 ? prm.ctas_per_sm : per_sm) * num_sms();
   if (g > cap) g = cap;
   if (g > prm.total_units) g = prm.total_units;
+  prm.grid = (int)g;
+  prm.split_q = prm.total_units / (int)g;
+  prm.split_r = prm.total_units % (int)g;
+  prm.ctas_per_unit = (float)g / (float)prm.total_units;
+  prm.div_grid = make_fastdiv((uint32_t)g);
+  prm.div_upi = make_fastdiv((uint32_t)prm.units_per_image_all);
   if (prm.pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)g);

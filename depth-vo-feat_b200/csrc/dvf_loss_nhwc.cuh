@@ -145,13 +145,11 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
 
   // balanced split (same unit list and bookkeeping as the image kernel, dvf_loss_kernel.cuh): this CTA owns units
   // [w, w_end) and walks them (image, level) by (image, level)
-  const int G = (int)gridDim.x, T = prm.total_units;
-  int w = (int)((long long)blockIdx.x * T / G);
-  const int w_end = (int)(((long long)blockIdx.x + 1) * T / G);
+  int w = split_start((int)blockIdx.x, prm);
+  const int w_end = split_start((int)blockIdx.x + 1, prm);
   pdl_let_successor_start(prm);
-  bool pdl_waited = false;
   while (w < w_end) {
-  const int b = w / prm.units_per_image_all;
+  const int b = (int)fastdiv((uint32_t)w, prm.div_upi);
   int l = 0;
   while (l + 1 < prm.n_levels && w - b * prm.units_per_image_all >= prm.lv[l + 1].unit_base) ++l;
   const LevelDev& lv = prm.lv[l];
@@ -159,10 +157,12 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
   const int real1 = real0 + lv.units_per_image;
   const int piece_end = min(w_end, real1);
   const int k0 = max(w, real0) - real0, k1 = piece_end - real0;   // units [k0, k1) of image b at level l
+  const bool piece_starts_here = w <= real0, piece_ends_here = piece_end == real1;
   w = piece_end;
   if (k1 <= k0) continue;   // only overhead units fell into my range (CTA-uniform)
-  const int first_cta = cta_of_unit(real0, G, T);
-  const int n_parts = cta_of_unit(real1 - 1, G, T) - first_cta + 1;
+  const int first_cta = piece_starts_here ? (int)blockIdx.x : cta_of_unit(real0, prm);
+  const int last_cta = piece_ends_here ? (int)blockIdx.x : cta_of_unit(real1 - 1, prm);
+  const int n_parts = last_cta - first_cta + 1;
   const int part = (int)blockIdx.x - first_cta;
   const int H = lv.H, W = lv.W, HW = lv.HW;
   const Geo geo = lv.geo;
@@ -407,9 +407,9 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
     acc[v][12] = acc_loss[v];
     acc[v][13] = acc[v][14] = acc[v][15] = 0.0f;
   }
-  pdl_wait_predecessor(prm, pdl_waited);
   reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, part, n_parts, b, C);
   }  // pieces of this CTA
+  pdl_wait_predecessor(prm);
 }
 
 template <int kV, bool kZeros>

@@ -73,11 +73,11 @@ typedef enum dvf_flags {
   DVF_FLAG_NO_TMA = 8,
   /* loss entries (image and channels-last kernels): programmatic dependent launch.  The launch carries the
    * programmatic-stream-serialisation attribute and lets its successor start early in turn, so that back-to-back
-   * loss launches (micro-batches, the views of a step, consecutive steps of a captured graph) overlap the serial
-   * tail of one launch (ticket, fp64 fold, pose backward) and the launch gap with the pixel work of the next.
-   * The kernel waits for the PREVIOUS kernel of the stream to complete before its first workspace access, but it
-   * reads its inputs and writes its gradient outputs before that.  CONTRACT: the previous kernel in the stream
-   * neither writes an input of this launch nor touches one of its outputs.                                   */
+   * loss launches (micro-batches, the views of a step, consecutive steps of a captured graph) overlap: the CTAs of
+   * launch i+1 start on the SM slots launch i frees while its last CTAs and its serial tail (ticket, fp64 fold,
+   * pose backward) still run.  The kernel does not wait for the PREVIOUS kernel of the stream until just before it
+   * exits.  CONTRACT: the previous kernel in the stream shares NO buffer with this launch -- it writes none of its
+   * inputs and touches none of its outputs, and the two launches use different workspaces.                    */
   DVF_FLAG_PDL = 16
 } dvf_flags;
 
