@@ -221,6 +221,13 @@ __device__ __forceinline__ float signed_unit(float d, float inv_n, bool gate) {
   return nz ? copysignf(inv_n, d) : 0.0f;
 }
 
+// -sign(d) * n with sign(0) = sign(NaN) = 0 (n >= 0, already gated: 0 for pixels without a valid sample).  One LOP3 for
+// the sign transfer (inverted sign bit of d onto |n|), one compare, one select.
+__device__ __forceinline__ float neg_signed_unit(float d, float n) {
+  const uint32_t r = (__float_as_uint(n) & 0x7fffffffu) | (~__float_as_uint(d) & 0x80000000u);
+  return (d < 0.0f || d > 0.0f) ? __uint_as_float(r) : 0.0f;
+}
+
 // Shared tail of the loss kernels: CTA fold of acc[kV][16], partial write, ticket, image fold, level fold.
 // `part` of `n_parts`: which of the CTA pieces of image b this is (fixed fold order => deterministic sums).
 // Does not return early: the image kernel calls it once per piece of its unit range.
@@ -646,9 +653,9 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
           }
           const Proj e = project_exact<kZeros>(&s_P[v][0], c1, &lv.geo);
           if (h == 0) {
-            pr.qz.x = e.qz; pr.nZ.x = -e.Z; pr.u.x = e.u; pr.v.x = e.v; pr.xn.x = e.xn; pr.yn.x = e.yn; pr.mxA = e.mx; pr.myA = e.my;
+            pr.qz.x = e.qz; pr.nZ.x = -e.Z; pr.u.x = e.u; pr.v.x = e.v; pr.xn.x = e.xn; pr.yn.x = e.yn;
           } else {
-            pr.qz.y = e.qz; pr.nZ.y = -e.Z; pr.u.y = e.u; pr.v.y = e.v; pr.xn.y = e.xn; pr.yn.y = e.yn; pr.mxB = e.mx; pr.myB = e.my;
+            pr.qz.y = e.qz; pr.nZ.y = -e.Z; pr.u.y = e.u; pr.v.y = e.v; pr.xn.y = e.xn; pr.yn.y = e.yn;
           }
         }
       }
@@ -695,23 +702,25 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
       accl[v] += (anyA ? lsA : 0.0f) + (anyB ? lsB : 0.0f);
       if (kGrad) {
         f2 gx = dup(0.0f), gy = dup(0.0f);
-        f2 su[kC];
+        // nsu = -sign(d1)/N (0 where d1 == 0 or the pixel has no valid sample): the gradient of the warped value
+        const f2 ngate = make_float2(anyA ? inv_n : 0.0f, anyB ? inv_n : 0.0f);
+        f2 nsu[kC];
 #pragma unroll
         for (int c = 0; c < kC; ++c) {
-          su[c] = make_float2(signed_unit(d1[c].x, inv_n, anyA), signed_unit(d1[c].y, inv_n, anyB));
-          const f2 g = kExpl ? mul2(su[c], ex) : su[c];
-          bilerp_grad2(t00[c], t01[c], t10[c], t11[c], L, neg2(g), gx, gy);
+          nsu[c] = make_float2(neg_signed_unit(d1[c].x, ngate.x), neg_signed_unit(d1[c].y, ngate.y));
+          const f2 ng = kExpl ? mul2(nsu[c], ex) : nsu[c];
+          bilerp_grad2(t00[c], t01[c], t10[c], t11[c], L, ng, gx, gy);
         }
         if (kExpl) {
-          if (gexpl_b) {
+          if (gexpl_b) {   // d/d mask = sum_c sign(d1) * d0 / N = -(nsu . d0), summed left to right like the reference
             if (liveA)
-              st_stream(gexpl_b + v * HW + idxA, add(add(mul(su[0].x, d0[0].x), mul(su[1].x, d0[1].x)), mul(su[2].x, d0[2].x)));
+              st_stream(gexpl_b + v * HW + idxA, -add(add(mul(nsu[0].x, d0[0].x), mul(nsu[1].x, d0[1].x)), mul(nsu[2].x, d0[2].x)));
             if (liveB)
-              st_stream(gexpl_b + v * HW + idxB, add(add(mul(su[0].y, d0[0].y), mul(su[1].y, d0[1].y)), mul(su[2].y, d0[2].y)));
+              st_stream(gexpl_b + v * HW + idxB, -add(add(mul(nsu[0].y, d0[0].y), mul(nsu[1].y, d0[1].y)), mul(nsu[2].y, d0[2].y)));
           }
         }
         ChainGrad2 cg;
-        chain_backward2(P, cam, pr, L, gx, gy, geo2, cg);
+        chain_backward2<kZeros>(P, cam, pr, L, gx, gy, geo2, cg);
         if (__builtin_expect(slow, 0)) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -731,8 +740,8 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
             p1.v = h == 0 ? pr.v.x : pr.v.y;
             p1.xn = h == 0 ? pr.xn.x : pr.xn.y;
             p1.yn = h == 0 ? pr.yn.x : pr.yn.y;
-            p1.mx = h == 0 ? pr.mxA : pr.mxB;
-            p1.my = h == 0 ? pr.myA : pr.myB;
+            p1.mx = kZeros && (h == 0 ? pr.xn.x : pr.xn.y) == 2.0f;
+            p1.my = kZeros && (h == 0 ? pr.yn.x : pr.yn.y) == 2.0f;
             L1.x0 = L1.y0 = 0;
             L1.w = L1.e = L1.n = L1.s = 0.0f;
             L1.bnw = L1.bne = L1.bsw = L1.bse = false;

@@ -76,7 +76,8 @@ __device__ __forceinline__ void pixel_to_cam2(const float* __restrict__ M, f2 d,
 
 struct Proj2 {
   f2 qz, nZ, rZ, u, v, xn, yn;   // nZ = -clamp(qz, 1e-3)
-  bool mxA, mxB, myA, myB;
+  // zeros padding: a coordinate that was overwritten (|x| > 1 -> 2, gradient killed) is recognised later by its value:
+  // it is exactly 2, which no coordinate that was kept (|x| <= 1 or NaN) can be -- no flag registers are carried
 };
 
 // hot path only (callers guard the operand range and patch lanes with the scalar exact routine)
@@ -95,14 +96,9 @@ __device__ __forceinline__ void project2(const float* __restrict__ P /*3x4, broa
   const f2 mone = dup(-1.0f);
   o.xn = add2(div_by2(add2(o.u, o.u), g.nW1, g.rW1), mone);
   o.yn = add2(div_by2(add2(o.v, o.v), g.nH1, g.rH1), mone);
-  o.mxA = o.mxB = o.myA = o.myB = false;
   if (kZeros) {
-    o.mxA = fabsf(o.xn.x) > 1.0f;
-    o.mxB = fabsf(o.xn.y) > 1.0f;
-    o.myA = fabsf(o.yn.x) > 1.0f;
-    o.myB = fabsf(o.yn.y) > 1.0f;
-    o.xn = make_float2(o.mxA ? 2.0f : o.xn.x, o.mxB ? 2.0f : o.xn.y);
-    o.yn = make_float2(o.myA ? 2.0f : o.yn.x, o.myB ? 2.0f : o.yn.y);
+    o.xn = make_float2(fabsf(o.xn.x) > 1.0f ? 2.0f : o.xn.x, fabsf(o.xn.y) > 1.0f ? 2.0f : o.xn.y);
+    o.yn = make_float2(fabsf(o.yn.x) > 1.0f ? 2.0f : o.yn.x, fabsf(o.yn.y) > 1.0f ? 2.0f : o.yn.y);
   }
 }
 
@@ -162,11 +158,14 @@ struct ChainGrad2 {
 };
 
 // hot path only
+template <bool kZeros>
 __device__ __forceinline__ void chain_backward2(const float* __restrict__ P, const Cam2& c, const Proj2& p, const Loc2& L,
                                                 f2 gx, f2 gy, const Geo2& g, ChainGrad2& o) {
   f2 gxn = mul2(gx, L.gmx), gyn = mul2(gy, L.gmy);
-  gxn = make_float2(p.mxA ? 0.0f : gxn.x, p.mxB ? 0.0f : gxn.y);
-  gyn = make_float2(p.myA ? 0.0f : gyn.x, p.myB ? 0.0f : gyn.y);
+  if (kZeros) {
+    gxn = make_float2(p.xn.x == 2.0f ? 0.0f : gxn.x, p.xn.y == 2.0f ? 0.0f : gxn.y);
+    gyn = make_float2(p.yn.x == 2.0f ? 0.0f : gyn.x, p.yn.y == 2.0f ? 0.0f : gyn.y);
+  }
   const f2 two = dup(2.0f);
   const f2 gu = mul2(div_by2(gxn, g.nW1, g.rW1), two);
   const f2 gv = mul2(div_by2(gyn, g.nH1, g.rH1), two);

@@ -208,9 +208,9 @@ __device__ __forceinline__ void pair_forward(const WarpParams& p, const float (&
       const Proj e = warp_project_exact<kZeros>(p.P + b * 12, c1, p.geo);
       Proj2& pr = x.pr;
       if (h == 0) {
-        pr.qz.x = e.qz; pr.nZ.x = -e.Z; pr.u.x = e.u; pr.v.x = e.v; pr.xn.x = e.xn; pr.yn.x = e.yn; pr.mxA = e.mx; pr.myA = e.my;
+        pr.qz.x = e.qz; pr.nZ.x = -e.Z; pr.u.x = e.u; pr.v.x = e.v; pr.xn.x = e.xn; pr.yn.x = e.yn;
       } else {
-        pr.qz.y = e.qz; pr.nZ.y = -e.Z; pr.u.y = e.u; pr.v.y = e.v; pr.xn.y = e.xn; pr.yn.y = e.yn; pr.mxB = e.mx; pr.myB = e.my;
+        pr.qz.y = e.qz; pr.nZ.y = -e.Z; pr.u.y = e.u; pr.v.y = e.v; pr.xn.y = e.xn; pr.yn.y = e.yn;
       }
     }
   }
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_c3x2_kernel(const _
       pb = ptr_off(pb, HW);
     }
     ChainGrad2 cg;
-    chain_backward2(P, x.cam, x.pr, L, gx, gy, geo2, cg);
+    chain_backward2<kZeros>(P, x.cam, x.pr, L, gx, gy, geo2, cg);
     if (__builtin_expect(!(x.fastA && x.fastB), 0)) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -336,8 +336,8 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_c3x2_kernel(const _
         p1.v = h == 0 ? pr.v.x : pr.v.y;
         p1.xn = h == 0 ? pr.xn.x : pr.xn.y;
         p1.yn = h == 0 ? pr.yn.x : pr.yn.y;
-        p1.mx = h == 0 ? pr.mxA : pr.mxB;
-        p1.my = h == 0 ? pr.myA : pr.myB;
+        p1.mx = kZeros && (h == 0 ? pr.xn.x : pr.xn.y) == 2.0f;
+        p1.my = kZeros && (h == 0 ? pr.yn.x : pr.yn.y) == 2.0f;
         L1.x0 = L1.y0 = 0;
         L1.w = L1.e = L1.n = L1.s = 0.0f;
         L1.bnw = L1.bne = L1.bsw = L1.bse = false;
