@@ -18,9 +18,10 @@ A step = the fused launch(es) of one loss evaluation with all gradients (pose_ve
 prologue, warp + loss + gradients over all levels and views, pose backward in the epilogue).  Image pyramids are
 prebuilt inputs.  Steps rotate over several distinct input sets whose total size exceeds L2; CUDA graphs
 hold --graph-steps consecutive steps.
-Multi-GPU: batch sharded, no data-path collective.  The loss terms are all-reduced EVERY step (NCCL, <= 16 floats) on a
-side stream inside the captured graph, so the exchange of step i overlaps the kernel of step i+1 as it would in a
-training loop that logs its loss.  The main value keeps the workload of --config at every N (C2: fixed batch per GPU =
+Multi-GPU: batch sharded, no data-path collective.  The loss terms (<= 16 floats) are exchanged EVERY step: by default
+fused into the loss kernel, whose epilogue stores the rank's terms into every peer's buffer over NVLink (an all-gather by
+peer-to-peer stores, dvf_b200.dist.PeerTerms; --exchange nccl: an NCCL all-reduce on a side stream inside the captured
+graph, which costs ~15 us per step because its kernel competes with the persistent loss kernel for SM slots).  The main value keeps the workload of --config at every N (C2: fixed batch per GPU =
 weak scaling, so that the driver's per-N efficiency compares like with like); when --config is C2 the line also carries
 `strong_c3`: the C3 workload at a FIXED global batch of 256 on the same N GPUs.
 """
@@ -84,7 +85,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip strong_c3 / unfused_gpu")
     ap.add_argument("--no-pdl", action="store_true", help="plain launches instead of programmatic dependent launches (A/B)")
-    ap.add_argument("--no-allreduce", action="store_true", help="N > 1: no per-step exchange of the loss terms (A/B)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl", "none"],
+                    help="N > 1, every step: p2p = the loss kernel stores its terms into every peer's buffer over NVLink (fused "
+                         "all-gather, dvf_b200.dist.PeerTerms; falls back to nccl if no peer mapping is available); nccl = "
+                         "all-reduce on a side stream inside the graph; none = no exchange (A/B)")
     ap.add_argument("--iid-depth", action="store_true", help="stress case: iid-noise depth instead of the smooth field")
     return ap.parse_args()
 
@@ -304,9 +308,18 @@ class Step:
             p.launch()
 
 
-def build_steps(wl, B, Bg, host, dev, sets, pdl):
+def build_steps(wl, B, Bg, host, dev, sets, pdl, peers=None, rank=0):
+    """peers: None, or a list that receives one dvf_b200.dist.PeerTerms per plan of a step (fused exchange of the terms)"""
     from dvf_b200 import ops
     from dvf_b200.plan import FusedLossPlan
+    from dvf_b200.dist import PeerTerms
+
+    def peer_kw(j, n_terms, k):
+        if peers is None:
+            return {}
+        if len(peers) <= j:
+            peers.append(PeerTerms(sets, n_terms, dev))
+        return dict(peer_terms=peers[j].slot_ptrs(k), peer_rank=rank)
     H, W, L, V = wl["H"], wl["W"], wl["levels"], wl["views"]
     sizes = [(H >> s, W >> s) for s in range(L)]
     ds = [float(1 << s) for s in range(L)]
@@ -318,14 +331,14 @@ def build_steps(wl, B, Bg, host, dev, sets, pdl):
         pose, K, Kinv = roll(host["pose"]), roll(host["K"]), roll(host["Kinv"])
         expl = [roll(x) for x in host["expl"]] if wl["expl"] else None
         plans = [FusedLossPlan(tgt_pyr, [[sp[l] for sp in src_pyrs] for l in range(L)], [roll(x) for x in host["depths"]],
-                               pose, K, Kinv, expl_levels=expl, downscales=ds, global_batch=Bg, pdl=pdl)]
+                               pose, K, Kinv, expl_levels=expl, downscales=ds, global_batch=Bg, pdl=pdl, **peer_kw(0, L * V, k))]
         f = wl.get("feature")
         if f:
             cl = lambda t: roll(t).to(torch.bfloat16 if f["dtype"] == "bf16" else torch.float32).contiguous(   # noqa: E731
                 memory_format=torch.channels_last)
             feats = [cl(x) for x in host["feat"]]
             plans.append(FusedLossPlan([feats[0]], [feats[1:]], [roll(host["feat_depth"])], pose, roll(host["feat_K"]),
-                                       roll(host["feat_Kinv"]), map_grads=True, global_batch=Bg, pdl=pdl))
+                                       roll(host["feat_Kinv"]), map_grads=True, global_batch=Bg, pdl=pdl, **peer_kw(1, V, k)))
         steps.append(Step(plans))
     return steps
 
@@ -451,17 +464,44 @@ def measure_workload(name, wl, args, world, rank, dev, sampler, steps_n, warmup_
     """value (K steps, device-timed, max over ranks) and, on request, the dominant kernel's roofline."""
     Bl, Bg = local_batch(wl, world, args.batch if name == args.config else 0)
     host = make_inputs(wl, Bl, seed=1000 + rank, smooth=not args.iid_depth)
-    steps = build_steps(wl, Bl, Bg, host, dev, args.sets, pdl=(args.sets >= 2 and not args.no_pdl))
-    runner = Runner(steps, args.graph_steps, world, not args.no_allreduce)
+    pdl = args.sets >= 2 and not args.no_pdl
+    mode, peers = (args.exchange if world > 1 else "none"), None
+    if mode == "p2p":
+        try:
+            peers = []
+            steps = build_steps(wl, Bl, Bg, host, dev, args.sets, pdl, peers=peers, rank=rank)
+        except RuntimeError as e:
+            if "peer-to-peer" not in str(e):
+                raise
+            mode, peers = "nccl", None
+    if peers is None:
+        steps = build_steps(wl, Bl, Bg, host, dev, args.sets, pdl)
+    runner = Runner(steps, args.graph_steps, world, mode == "nccl")
+    if mode == "p2p":
+        runner.exchange = (f"fused into the loss kernel: every step its epilogue stores the rank's loss terms into every peer's buffer "
+                           f"over NVLink (all-gather by peer-to-peer stores, mapping via {peers[0].how}); no collective launch")
     wpx = steps[0].warped_px
     assert wpx == warped_px(wl, Bl)
     t0 = time.time()
     runner.spin(args.prewarm_ms)
     runner.run(max(warmup_n, 3))
     ms_total = timed(runner, steps_n, world, dev)
+    xcheck = None
+    if world > 1 and mode != "none":
+        # what every rank holds for the LAST step against an NCCL all-reduce of the same terms (outside the timed region)
+        import torch.distributed as dist
+        last = (steps_n - 1) % args.sets
+        mine = torch.cat([p.terms for p in steps[last].plans]).clone()
+        ref = mine.clone()
+        dist.all_reduce(ref)
+        if mode == "p2p":
+            got = torch.cat([pt.gathered(last).sum(0) for pt in peers])
+        else:
+            got = runner.xbuf[(steps_n - 1) % runner.graph_steps] if steps_n % runner.graph_steps == 0 else ref
+        xcheck = float(((got - ref).abs().max() / ref.abs().max()).item())
     out = {"value": wpx * world * steps_n / (ms_total * 1e-3), "ms_per_step": ms_total / steps_n, "steps": steps_n,
            "warped_px_per_step_per_gpu": wpx, "gpu_launches": steps[0].n_launches * steps_n,
-           "exchange": runner.exchange, "set_bytes": steps[0].bytes, "batch_per_gpu": Bl, "global_batch": Bg}
+           "exchange": runner.exchange, "exchange_check_rel_err": xcheck, "set_bytes": steps[0].bytes, "batch_per_gpu": Bl, "global_batch": Bg}
     roof = None
     if roofline:
         dom = Runner(steps, args.graph_steps, 1, False, only=lambda s: s.dominant)
@@ -649,6 +689,7 @@ def run_b200(args):
         extras["strong_c3"] = {"metric": METRIC, "value": s_out["value"], "unit": UNIT, "scaling": "strong", "n_gpus": world,
                                "ms_per_step": s_out["ms_per_step"], "steps": s_out["steps"], "global_batch": s_out["global_batch"],
                                "batch_per_gpu": s_out["batch_per_gpu"], "exchange": s_out["exchange"],
+                               "exchange_check_rel_err": s_out["exchange_check_rel_err"],
                                "workload": c3["title"], "roofline": s_roof}
     if not args.no_extras and rank == 0:
         try:
@@ -675,7 +716,7 @@ def run_b200(args):
                                f"{args.graph_steps} consecutive steps" + ("" if (args.no_pdl or args.sets < 2) else
                                "; consecutive steps work on disjoint input sets and are chained by programmatic dependent launch "
                                "(DVF_FLAG_PDL): the serial tail of step i overlaps the pixel work of step i+1"),
-                       "exchange": main["exchange"]},
+                       "exchange": main["exchange"], "exchange_check_rel_err": main["exchange_check_rel_err"]},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": main["gpu_launches"], "warped_px_per_step_per_gpu": main["warped_px_per_step_per_gpu"],
         }

@@ -171,6 +171,15 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
   prm.nan_flags = (d->flags & DVF_FLAG_NAN_CHECK) ? d->nan_flags : nullptr;
   if ((d->flags & DVF_FLAG_NAN_CHECK) && !d->nan_flags) return DVF_EINVAL_NULL;
   prm.ctas_per_sm = d->ctas_per_sm;
+  if (d->n_peers < 0 || d->n_peers > DVF_MAX_PEERS || (d->n_peers > 0 && (d->peer_rank < 0 || d->peer_rank >= d->n_peers)))
+    return DVF_EINVAL_SHAPE;
+  if (d->n_peers > 0 && !d->peer_terms) return DVF_EINVAL_NULL;
+  prm.n_peers = d->n_peers;
+  prm.peer_rank = d->peer_rank;
+  for (int q = 0; q < DVF_MAX_PEERS; ++q) {
+    prm.peer_terms[q] = q < d->n_peers ? d->peer_terms[q] : nullptr;
+    if (q < d->n_peers && (!prm.peer_terms[q] || !aligned(prm.peer_terms[q], 4))) return DVF_EINVAL_NULL;
+  }
   prm.pdl = (d->flags & DVF_FLAG_PDL) ? 1 : 0;
   if (d->grad_dtype != DVF_F32) return DVF_EUNSUPPORTED;   // TODO bf16 map gradients
   prm.grad_bf16 = d->grad_dtype == DVF_BF16;

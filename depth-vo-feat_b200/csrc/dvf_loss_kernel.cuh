@@ -96,6 +96,9 @@ struct LossParams {
   FastDiv div_grid, div_upi;   // division by G and by units_per_image_all
   const float* upstream;   // device scalar multiplying every gradient, or nullptr (= 1)
   int* nan_flags;          // nullptr, or a word that collects bit l*V+v when term (l, v) is NaN
+  // fused exchange of the loss terms (dvf_loss_desc.peer_terms): row peer_rank of every peer's [n_peers][n_levels*V] buffer
+  int n_peers, peer_rank;
+  float* peer_terms[DVF_MAX_PEERS];
   // pose mode (dvf_photo_loss_fused_pose): P / K^-1_s are derived in the CTA prologue, d pose in the epilogue
   const float* pose_vec;   // [B,V,6] or nullptr
   const float* K;          // [B,3,3]
@@ -363,6 +366,11 @@ __device__ __forceinline__ void reduce_and_finish(float (&acc)[kV][kRedSlots], c
           const float term = (float)(t / ((double)prm.mean_batch * (double)C * (double)lv.HW));
           prm.terms[l * kV + v] = term;
           if (prm.nan_flags && term != term) atomicOr(prm.nan_flags, 1 << ((l * kV + v) & 31));
+          // all-gather over NVLink: one remote store per peer, fire and forget (nobody waits for it here)
+          for (int q = 0; q < prm.n_peers; ++q)
+            asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(prm.peer_terms[q] + (size_t)prm.peer_rank * prm.n_levels * kV + l * kV + v),
+                         "f"(term)
+                         : "memory");
         }
         __syncthreads();
       }

@@ -430,6 +430,92 @@ __global__ void __launch_bounds__(kThreads) cam2pixel_kernel(const float* __rest
   reinterpret_cast<float2*>(grid)[(size_t)b * HW + idx] = make_float2(xn, yn);
 }
 
+// backward of pixel2cam w.r.t. depth: autograd of `cam = ray * depth.unsqueeze(1)` is (g_cam * ray).sum(1), left to right
+__global__ void __launch_bounds__(kThreads) pixel2cam_bwd_kernel(const float* __restrict__ gcam, const float* __restrict__ Kinv,
+                                                                 int HW, FastDiv divW, int W, float* __restrict__ gdepth) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= HW) return;
+  float M[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) M[k] = __ldg(Kinv + b * 9 + k);
+  const int i = (int)fastdiv((uint32_t)idx, divW), j = idx - i * W;
+  Cam c;
+  pixel_to_cam(M, 1.0f, i, j, c);
+  float g = mul(gcam[((size_t)b * 3 + 0) * HW + idx], c.ray[0]);
+  g = add(g, mul(gcam[((size_t)b * 3 + 1) * HW + idx], c.ray[1]));
+  g = add(g, mul(gcam[((size_t)b * 3 + 2) * HW + idx], c.ray[2]));
+  gdepth[(size_t)b * HW + idx] = g;
+}
+
+// backward of cam2pixel: g_grid [B,H,W,2] -> g_cam [B,3,H,W] (written), g_rot [B,3,3] and g_tr [B,3] (zero-filled by the
+// entry, accumulated: one shuffle fold per warp, one atomic per warp and entry).  Same fp32 sequence as autograd's:
+// overwritten coordinates pass no gradient, /(w-1), *2, d(X/Z), clamp pass-through, rot^T.
+__global__ void __launch_bounds__(kThreads) cam2pixel_bwd_kernel(const float* __restrict__ ggrid, const float* __restrict__ cam,
+                                                                 const float* __restrict__ rot, const float* __restrict__ tr,
+                                                                 int H, int W, int HW, int zeros, float* __restrict__ gcam,
+                                                                 float* __restrict__ grot, float* __restrict__ gtr) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * kThreads + threadIdx.x;
+  const bool live = idx < HW;
+  float c[3] = {0.0f, 0.0f, 1.0f}, q[3], gq[3] = {0.0f, 0.0f, 0.0f};
+  float R[9] = {1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f};
+  if (rot) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = __ldg(rot + b * 9 + k);
+  }
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = cam[((size_t)b * 3 + k) * HW + idx];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float v = rot ? dot3(R[k * 3], R[k * 3 + 1], R[k * 3 + 2], c[0], c[1], c[2]) : c[k];
+      q[k] = tr ? add(v, __ldg(tr + b * 3 + k)) : v;
+    }
+    const float Z = (q[2] < kMinDepthZ) ? kMinDepthZ : q[2];
+    const float u = div(q[0], Z), v = div(q[1], Z);
+    const float xn = sub(div(mul(2.0f, u), (float)(W - 1)), 1.0f);
+    const float yn = sub(div(mul(2.0f, v), (float)(H - 1)), 1.0f);
+    const float2 g = reinterpret_cast<const float2*>(ggrid)[(size_t)b * HW + idx];
+    const float gxn = (zeros && (xn > 1.0f || xn < -1.0f)) ? 0.0f : g.x;
+    const float gyn = (zeros && (yn > 1.0f || yn < -1.0f)) ? 0.0f : g.y;
+    const float gu = mul(div(gxn, (float)(W - 1)), 2.0f), gv = mul(div(gyn, (float)(H - 1)), 2.0f);
+    gq[0] = div(gu, Z);
+    gq[1] = div(gv, Z);
+    const float gZ = add(mul(-gu, div(u, Z)), mul(-gv, div(v, Z)));
+    gq[2] = (q[2] >= kMinDepthZ) ? gZ : 0.0f;
+    if (gcam) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        gcam[((size_t)b * 3 + k) * HW + idx] = rot ? dot3(R[k], R[3 + k], R[6 + k], gq[0], gq[1], gq[2]) : gq[k];
+    }
+  }
+  if (grot || gtr) {
+    float t[12];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[r * 4 + k] = live ? gq[r] * c[k] : 0.0f;
+      t[r * 4 + 3] = live ? gq[r] : 0.0f;
+    }
+#pragma unroll
+    for (int s = 0; s < 12; ++s) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t[s] += __shfl_xor_sync(0xffffffffu, t[s], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        if (grot) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) atomicAdd(grot + b * 9 + r * 3 + k, t[r * 4 + k]);
+        }
+        if (gtr) atomicAdd(gtr + b * 3 + r, t[r * 4 + 3]);
+      }
+    }
+  }
+}
+
 static int fill_params(const dvf_desc* d, WarpParams& p) {
   if (!d) return DVF_EINVAL_NULL;
   if (d->B <= 0 || d->C <= 0 || d->H <= 0 || d->W <= 0 || (long long)d->H * d->W >= (1ll << 30)) return DVF_EINVAL_SHAPE;
@@ -548,5 +634,32 @@ DVF_EXPORT int dvf_cam2pixel(const float* cam, const float* rot, const float* tr
   const int HW = H * W;
   dim3 grid((HW + kThreads - 1) / kThreads, B);
   cam2pixel_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(cam, rot, tr, H, W, HW, padding == DVF_PAD_ZEROS, grid_out);
+  return launch_status();
+}
+
+DVF_EXPORT int dvf_pixel2cam_bwd(const float* gcam, const float* Kinv, int32_t B, int32_t H, int32_t W, float* gdepth,
+                                 void* stream) {
+  if (!gcam || !Kinv || !gdepth) return DVF_EINVAL_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || (long long)H * W >= (1ll << 30)) return DVF_EINVAL_SHAPE;
+  const int HW = H * W;
+  dim3 grid((HW + kThreads - 1) / kThreads, B);
+  pixel2cam_bwd_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(gcam, Kinv, HW, make_fastdiv((uint32_t)W), W, gdepth);
+  return launch_status();
+}
+
+DVF_EXPORT int dvf_cam2pixel_bwd(const float* ggrid, const float* cam, const float* rot, const float* tr, int32_t B, int32_t H,
+                                 int32_t W, int32_t padding, float* gcam, float* grot, float* gtr, void* stream) {
+  if (!ggrid || !cam) return DVF_EINVAL_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || (long long)H * W >= (1ll << 30)) return DVF_EINVAL_SHAPE;
+  if (padding != DVF_PAD_ZEROS && padding != DVF_PAD_BORDER) return DVF_EINVAL_DTYPE;
+  if (!aligned(ggrid, 8)) return DVF_EINVAL_ALIGN;
+  if (grot && !rot) return DVF_EINVAL_NULL;
+  if (gtr && !tr) return DVF_EINVAL_NULL;
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  if (grot && cudaMemsetAsync(grot, 0, sizeof(float) * 9 * B, cs) != cudaSuccess) return launch_status();
+  if (gtr && cudaMemsetAsync(gtr, 0, sizeof(float) * 3 * B, cs) != cudaSuccess) return launch_status();
+  const int HW = H * W;
+  dim3 grid((HW + kThreads - 1) / kThreads, B);
+  cam2pixel_bwd_kernel<<<grid, kThreads, 0, cs>>>(ggrid, cam, rot, tr, H, W, HW, padding == DVF_PAD_ZEROS, gcam, grot, gtr);
   return launch_status();
 }

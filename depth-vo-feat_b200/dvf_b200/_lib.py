@@ -53,7 +53,8 @@ class dvf_loss_desc(C.Structure):
     _fields_ = [("B", C.c_int32), ("C", C.c_int32), ("V", C.c_int32), ("n_levels", C.c_int32),
                 ("dtype", C.c_int32), ("layout", C.c_int32), ("padding", C.c_int32), ("flags", C.c_int32),
                 ("mean_batch", C.c_int32), ("grad_dtype", C.c_int32), ("piece_overhead", C.c_int32), ("ctas_per_sm", C.c_int32),
-                ("upstream", C.c_void_p), ("nan_flags", C.c_void_p)]
+                ("upstream", C.c_void_p), ("nan_flags", C.c_void_p),
+                ("n_peers", C.c_int32), ("peer_rank", C.c_int32), ("peer_terms", C.POINTER(C.c_void_p))]
 
 
 _vp, _i32, _sz, _fp = C.c_void_p, C.c_int32, C.c_size_t, C.POINTER(C.c_float)
@@ -66,6 +67,8 @@ SIGNATURES = {
     "dvf_pose_proj_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _fp, _i32, _vp, _vp]),
     "dvf_pixel2cam": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "dvf_cam2pixel": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "dvf_pixel2cam_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "dvf_cam2pixel_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "dvf_inverse_warp_fwd": (C.c_int, [C.POINTER(dvf_desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dvf_inverse_warp_bwd_workspace_bytes": (_sz, [C.POINTER(dvf_desc)]),
     "dvf_inverse_warp_bwd": (C.c_int, [C.POINTER(dvf_desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -280,31 +280,84 @@ class InverseWarp(torch.autograd.Function):
         return gimg, (gdepth if ctx.needs_input_grad[1] else None), gpose, None, None, None, None
 
 
+class Pixel2Cam(torch.autograd.Function):
+    """pixel2cam (inverse_warp.py:26-40): depth [B,H,W], K^-1 [B,3,3] -> camera-frame points [B,3,H,W]; differentiable
+    w.r.t. depth (the intrinsics are data in the reference)."""
+
+    @staticmethod
+    def forward(ctx, depth, intrinsics_inv):
+        lib = _lib.load()
+        depth, Kinv = _req(depth, "depth", 3), _req(intrinsics_inv, "intrinsics_inv", 3)
+        if ctx.needs_input_grad[1]:
+            raise DvfError("gradients w.r.t. the camera intrinsics are not implemented (unused by the reference)")
+        B, H, W = depth.shape
+        cam = torch.empty(B, 3, H, W, device=depth.device, dtype=torch.float32)
+        with _same_device(depth, Kinv):
+            _lib.check(lib.dvf_pixel2cam(_ptr(depth), _ptr(Kinv), B, H, W, _ptr(cam), _stream()), "dvf_pixel2cam")
+        ctx.save_for_backward(Kinv)
+        return cam
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gcam):
+        lib = _lib.load()
+        (Kinv,) = ctx.saved_tensors
+        g = _req(gcam, "grad_cam", 4)
+        B, _, H, W = g.shape
+        gdepth = torch.empty(B, H, W, device=g.device, dtype=torch.float32)
+        with _same_device(g, Kinv):
+            _lib.check(lib.dvf_pixel2cam_bwd(_ptr(g), _ptr(Kinv), B, H, W, _ptr(gdepth), _stream()), "dvf_pixel2cam_bwd")
+        return gdepth, None
+
+
 def pixel2cam(depth, intrinsics_inv):
-    """pixel2cam (inverse_warp.py:26-40), forward only."""
-    lib = _lib.load()
-    depth, Kinv = _req(depth, "depth", 3), _req(intrinsics_inv, "intrinsics_inv", 3)
-    if torch.is_grad_enabled() and (depth.requires_grad or Kinv.requires_grad):
-        raise DvfError("stand-alone pixel2cam is forward-only; differentiate through inverse_warp instead")
-    B, H, W = depth.shape
-    cam = torch.empty(B, 3, H, W, device=depth.device, dtype=torch.float32)
-    _lib.check(lib.dvf_pixel2cam(_ptr(depth), _ptr(Kinv), B, H, W, _ptr(cam), _stream()), "dvf_pixel2cam")
-    return cam
+    """pixel2cam (inverse_warp.py:26-40)."""
+    return Pixel2Cam.apply(depth, intrinsics_inv)
+
+
+class Cam2Pixel(torch.autograd.Function):
+    """cam2pixel (inverse_warp.py:43-74): [B,3,H,W] points, optional rotation [B,3,3] and translation [B,3,1] -> sampling
+    grid [B,H,W,2]; differentiable w.r.t. all three."""
+
+    @staticmethod
+    def forward(ctx, cam_coords, proj_c2p_rot, proj_c2p_tr, padding_mode):
+        lib = _lib.load()
+        cam = _req(cam_coords, "cam_coords", 4)
+        rot = None if proj_c2p_rot is None else _req(proj_c2p_rot, "proj_c2p_rot", 3)
+        tr = None if proj_c2p_tr is None else _req(proj_c2p_tr, "proj_c2p_tr").reshape(cam.shape[0], 3).contiguous()
+        B, _, H, W = cam.shape
+        grid = torch.empty(B, H, W, 2, device=cam.device, dtype=torch.float32)
+        with _same_device(cam, rot, tr):
+            _lib.check(lib.dvf_cam2pixel(_ptr(cam), _ptr(rot), _ptr(tr), B, H, W, PADDING[padding_mode], _ptr(grid), _stream()),
+                       "dvf_cam2pixel")
+        ctx.save_for_backward(cam, *[t for t in (rot, tr) if t is not None])
+        ctx.meta = (rot is not None, tr is not None, padding_mode, None if proj_c2p_tr is None else tuple(proj_c2p_tr.shape))
+        return grid
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, ggrid):
+        lib = _lib.load()
+        has_rot, has_tr, padding_mode, tr_shape = ctx.meta
+        saved = list(ctx.saved_tensors)
+        cam = saved.pop(0)
+        rot = saved.pop(0) if has_rot else None
+        tr = saved.pop(0) if has_tr else None
+        g = _req(ggrid, "grad_grid", 4)
+        B, _, H, W = cam.shape
+        need_cam, need_rot, need_tr = ctx.needs_input_grad[0], has_rot and ctx.needs_input_grad[1], has_tr and ctx.needs_input_grad[2]
+        gcam = torch.empty_like(cam) if need_cam else None
+        grot = torch.empty(B, 3, 3, device=cam.device, dtype=torch.float32) if need_rot else None
+        gtr = torch.empty(B, 3, device=cam.device, dtype=torch.float32) if need_tr else None
+        with _same_device(g, cam, rot, tr):
+            _lib.check(lib.dvf_cam2pixel_bwd(_ptr(g), _ptr(cam), _ptr(rot), _ptr(tr), B, H, W, PADDING[padding_mode], _ptr(gcam),
+                                             _ptr(grot), _ptr(gtr), _stream()), "dvf_cam2pixel_bwd")
+        return gcam, grot, (None if gtr is None else gtr.reshape(tr_shape)), None
 
 
 def cam2pixel(cam_coords, proj_c2p_rot, proj_c2p_tr, padding_mode):
-    """cam2pixel (inverse_warp.py:43-74), forward only."""
-    lib = _lib.load()
-    cam = _req(cam_coords, "cam_coords", 4)
-    rot = None if proj_c2p_rot is None else _req(proj_c2p_rot, "proj_c2p_rot", 3)
-    tr = None if proj_c2p_tr is None else _req(proj_c2p_tr, "proj_c2p_tr").reshape(cam.shape[0], 3).contiguous()
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (cam_coords, proj_c2p_rot, proj_c2p_tr)):
-        raise DvfError("stand-alone cam2pixel is forward-only; differentiate through inverse_warp instead")
-    B, _, H, W = cam.shape
-    grid = torch.empty(B, H, W, 2, device=cam.device, dtype=torch.float32)
-    _lib.check(lib.dvf_cam2pixel(_ptr(cam), _ptr(rot), _ptr(tr), B, H, W, PADDING[padding_mode], _ptr(grid), _stream()),
-               "dvf_cam2pixel")
-    return grid
+    """cam2pixel (inverse_warp.py:43-74)."""
+    return Cam2Pixel.apply(cam_coords, proj_c2p_rot, proj_c2p_tr, padding_mode)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -462,7 +515,7 @@ class _LossCall:
                 up = upstream.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
             d = dvf_loss_desc(B, Cc, V, L, self.dtype, self.layout, PADDING[cfg.padding_mode], flags,
                               int(cfg.global_batch or 0), _lib.F32, 0, 0, _ptr(up),
-                              nan_flags(dev).data_ptr() if cfg.nan_check else None)
+                              nan_flags(dev).data_ptr() if cfg.nan_check else None, 0, 0, None)
             nbytes = lib.dvf_photo_loss_workspace_bytes(C.byref(d), levels)
             if nbytes == 0:
                 raise DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")

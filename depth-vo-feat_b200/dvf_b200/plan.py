@@ -26,12 +26,15 @@ class FusedLossPlan:
                  rotation_mode: str = "euler", padding_mode: str = "zeros", need_grad: bool = True,
                  map_grads: bool = False, global_batch: Optional[int] = None, align_corners: bool = False,
                  upstream: Optional[torch.Tensor] = None, fused_pose: bool = True, use_tma: bool = True,
-                 piece_overhead: int = 0, ctas_per_sm: int = 0, pdl: bool = False):
+                 piece_overhead: int = 0, ctas_per_sm: int = 0, pdl: bool = False,
+                 peer_terms: Optional[Sequence[int]] = None, peer_rank: int = 0):
         """Maps: dense NCHW fp32 (images, any C) or channels-last fp32 / bf16 feature maps ([B,C,H,W] tensors in
         torch.channels_last memory).  map_grads: also produce d/d tgt and d/d src (fp32, layout of the maps).
         global_batch: this plan holds B of the global_batch images of a sharded batch (dvf_loss_desc.mean_batch).
         upstream: device scalar multiplying every gradient (dvf_loss_desc.upstream).
-        pdl: programmatic dependent launch (DVF_FLAG_PDL): back-to-back launches of plans with DISJOINT buffers overlap."""
+        pdl: programmatic dependent launch (DVF_FLAG_PDL): back-to-back launches of plans with DISJOINT buffers overlap.
+        peer_terms: device pointers (as mapped in this process) of every rank's [n_peers][L*V] exchange buffer; the kernel
+        epilogue stores this rank's loss terms into row peer_rank of each (dvf_b200.dist.PeerTerms)."""
         from .ops import _nhwc_ok
         self.lib = _lib.load()
         dev = pose.device
@@ -88,7 +91,11 @@ class FusedLossPlan:
         flags = (_lib.FLAG_ALIGN_CORNERS if align_corners else 0) | (_lib.FLAG_ZERO_GSRC if self.map_grads else 0) | \
                 (0 if use_tma else _lib.FLAG_NO_TMA) | (_lib.FLAG_PDL if pdl else 0)
         self.desc = dvf_loss_desc(B, Cc, V, L, dtype, layout, PADDING[padding_mode], flags, int(global_batch or 0), _lib.F32,
-                                  int(piece_overhead), int(ctas_per_sm), None if upstream is None else upstream.data_ptr(), None)
+                                  int(piece_overhead), int(ctas_per_sm), None if upstream is None else upstream.data_ptr(), None,
+                                  0, 0, None)
+        if peer_terms:
+            self._peer_arr = (C.c_void_p * len(peer_terms))(*[int(x) for x in peer_terms])   # keep alive
+            self.desc.n_peers, self.desc.peer_rank, self.desc.peer_terms = len(peer_terms), int(peer_rank), self._peer_arr
         n = self.lib.dvf_photo_loss_workspace_bytes(C.byref(self.desc), self.levels)
         if n == 0:
             raise _lib.DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")

@@ -124,6 +124,13 @@ int dvf_cam2pixel(const float* cam /*[B,3,H,W]*/, const float* rot /*[B,3,3] den
                   const float* tr /*[B,3] dense, nullable*/, int32_t B, int32_t H, int32_t W,
                   int32_t padding, float* grid /*[B,H,W,2]*/, void* stream);
 
+/* Their backward passes (the reference differentiates them through autograd): d depth = (g_cam * ray).sum(1);
+ * g_grid [B,H,W,2] -> g_cam [B,3,H,W], g_rot [B,3,3], g_tr [B,3] (each nullable; g_rot / g_tr need rot / tr).     */
+int dvf_pixel2cam_bwd(const float* gcam /*[B,3,H,W]*/, const float* Kinv, int32_t B, int32_t H, int32_t W,
+                      float* gdepth /*[B,H,W]*/, void* stream);
+int dvf_cam2pixel_bwd(const float* ggrid /*[B,H,W,2]*/, const float* cam /*[B,3,H,W]*/, const float* rot, const float* tr,
+                      int32_t B, int32_t H, int32_t W, int32_t padding, float* gcam, float* grot, float* gtr, void* stream);
+
 /* ---- inverse_warp (inverse_warp.py:160-193) ------------------------------
  * warped = grid_sample(img, cam2pixel(pixel2cam(depth,Kinv), P), padding),
  * P = K @ pose_vec2mat(pose) [B,3,4].  valid (nullable, uint8 [B,H,W]) is the
@@ -180,7 +187,17 @@ typedef struct dvf_loss_desc {
   const float* upstream;  /* device scalar g = d(total)/d(sum of terms): every gradient is scaled by it
                              (terms are not); NULL = 1                                              */
   int32_t* nan_flags;     /* device word for DVF_FLAG_NAN_CHECK, OR-ed into (never cleared); nullable */
+  /* Exchange of the loss terms between the GPUs of a node, fused into the kernel's epilogue (multi-GPU logging of
+   * the loss): the CTA that finishes a level stores its terms into the buffer of EVERY peer over
+   * NVLink (peer-to-peer mapped memory), so each rank ends up with all ranks' terms -- an all-gather without a
+   * collective launch; the global term is the sum over the rows.  peer_terms: HOST array of n_peers device
+   * pointers, entry q = rank q's buffer [n_peers][n_levels*V] floats as mapped in THIS process; this launch writes
+   * row peer_rank of every buffer.  Visible to a peer once this kernel has completed (stream / event / barrier
+   * order).  n_peers = 0: no exchange.                                                                         */
+  int32_t n_peers, peer_rank;
+  float* const* peer_terms;
 } dvf_loss_desc;
+#define DVF_MAX_PEERS 8
 
 size_t dvf_photo_loss_workspace_bytes(const dvf_loss_desc* d, const dvf_level* levels);
 
