@@ -2,8 +2,11 @@
 
 The multi-scale, multi-view, explainability-weighted photometric loss is ONE fused CUDA launch over
 all scales and views (csrc/dvf_loss.cu) preceded by one pass that builds the 'area' pyramids
-(csrc/dvf_aux.cu).  The NaN assertion of the reference (:34, a device sync per view and scale) is
-not replicated; NaNs propagate into the returned loss.  CUDA tensors only.
+(csrc/dvf_aux.cu).  The NaN assertion of the reference (:34, a device synchronisation per view and scale)
+becomes an in-kernel flag: with NAN_CHECK = True the launch ORs bit level*V+view into a device word when
+that loss term is NaN, and assert_no_nan() -- called whenever the training loop likes, e.g. once per
+logging interval -- performs the reference's assertion with ONE synchronisation.  NaNs propagate into the
+returned loss either way.  CUDA tensors only.
 """
 from __future__ import division
 
@@ -12,6 +15,18 @@ from torch import nn
 
 from dvf_b200 import ops as _ops
 from inverse_warp import inverse_warp  # noqa: F401  (re-exported like the reference, :6)
+
+
+NAN_CHECK = False   # True: collect NaN loss terms in dvf_b200.ops.nan_flags() (DVF_FLAG_NAN_CHECK)
+
+
+def assert_no_nan():
+    """The reference's `assert((reconstruction_loss == reconstruction_loss).item() == 1)` (:34) for every loss term
+    computed since the flags were last cleared; clears them."""
+    flags = _ops.nan_flags()
+    bits = int(flags.item())
+    flags.zero_()
+    assert bits == 0, "NaN reconstruction loss at (scale, view) bits {:#b}".format(bits)
 
 
 def _as_list(x):
@@ -38,7 +53,7 @@ def photometric_reconstruction_loss(tgt_img, ref_imgs, intrinsics, intrinsics_in
     src_levels = [[ref_pyr[v][l] for v in range(len(ref_imgs))] for l in range(n)]
     loss, _ = _ops.fused_photo_loss(tgt_pyr, src_levels, [d[:, 0] for d in depths], pose, intrinsics, intrinsics_inv,
                                     expl_levels=masks if has_mask else None, downscales=downscales,
-                                    rotation_mode=rotation_mode, padding_mode=padding_mode)
+                                    rotation_mode=rotation_mode, padding_mode=padding_mode, nan_check=NAN_CHECK)
     return loss
 
 

@@ -19,7 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libdvf_oracle.so")
 
-PAD = {"zeros": 0, "border": 1}
+PAD = {"zeros": 0, "border": 1, "zeros_align": 2, "border_align": 3}   # *_align: grid_sample(align_corners=True)
 ROT = {"euler": 0, "quat": 1}
 
 

@@ -189,7 +189,7 @@ static inline void chain_fwd(const float *P /*3x4*/, const float *M /*3x3*/,
   o->xn = (2.0f * o->u) / (float)(W - 1) - 1.0f;
   o->yn = (2.0f * o->v) / (float)(H - 1) - 1.0f;
   o->mx = o->my = 0;
-  if (padding == DVFO_PAD_ZEROS) {
+  if ((padding & 1) == DVFO_PAD_ZEROS) {
     if (o->xn > 1.0f || o->xn < -1.0f) { o->xn = 2.0f; o->mx = 1; }
     if (o->yn > 1.0f || o->yn < -1.0f) { o->yn = 2.0f; o->my = 1; }
   }
@@ -205,17 +205,22 @@ typedef struct {
   float w, e, n, s;   /* w = ix-x0, e = 1-w, n = iy-y0, s = 1-n            */
 } samp_loc;
 
-static inline float unnormalize(float c, int size) {
+/* padding arguments carry the grid_sample convention in bit 1: DVFO_ALIGN_CORNERS = align_corners=True (the torch <= 1.2
+ * behaviour the reference was written for; ATen ComputeLocation: (x+1) * ((size-1)/2), one rounded product) */
+#define DVFO_ALIGN_CORNERS 2
+static inline float unnormalize(float c, int size, int align_corners) {
+  if (align_corners) return (c + 1.0f) * ((float)(size - 1) / 2.0f);
   return fmaf(c + 1.0f, (float)size / 2.0f, -0.5f);
 }
 
 static inline void locate(float xn, float yn, int H, int W, int padding,
                           samp_loc *L) {
-  L->ix = unnormalize(xn, W);
-  L->iy = unnormalize(yn, H);
-  L->gmx = (float)W / 2.0f;
-  L->gmy = (float)H / 2.0f;
-  if (padding == DVFO_PAD_BORDER) {
+  const int ac = (padding & DVFO_ALIGN_CORNERS) != 0;
+  L->ix = unnormalize(xn, W, ac);
+  L->iy = unnormalize(yn, H, ac);
+  L->gmx = ac ? (float)(W - 1) / 2.0f : (float)W / 2.0f;
+  L->gmy = ac ? (float)(H - 1) / 2.0f : (float)H / 2.0f;
+  if ((padding & 1) == DVFO_PAD_BORDER) {
     /* clip_coordinates(_set_grad), ATen/native/GridSampler.h */
     float mxv = (float)(W - 1), myv = (float)(H - 1);
     if (L->ix <= 0.0f) { L->ix = 0.0f; L->gmx = 0.0f; }

@@ -48,6 +48,19 @@ def _reset(mods):
             m.pixel_coords = None
 
 
+class _align_corners_true:
+    """Run the (unmodified) reference with F.grid_sample(align_corners=True): the sampling convention of torch <= 1.2,
+    which the reference was written for and never states (inverse_warp.py:191 passes no align_corners)."""
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self.F, self.orig = F, F.grid_sample
+        F.grid_sample = lambda img, grid, *a, **k: self.orig(img, grid, *a, **{**k, "align_corners": True})
+
+    def __exit__(self, *exc):
+        self.F.grid_sample = self.orig
+
+
 def case_inverse_warp(mods, name, B, C, H, W, kind, rot, pad, seed, smooth=True, feature=False):
     iw = mods["loss_functions"] if C != 3 else mods["inverse_warp"]   # the copy in loss_functions accepts any C
     d = syn.stereo_temporal_batch(B, H, W, seed=seed, C=C, smooth=smooth, temporal=kind if kind != "stereo" else "kitti",
@@ -249,6 +262,10 @@ def main():
     case_regularisers(mods, "regularisers", 2, 30, 52, 3, seed=13)
     case_trig("trig_f32", 1 << 17, seed=14)
     case_config1(mods, "config1_4x3x128x416", 4, 128, 416, seed=15)
+    with _align_corners_true():
+        case_inverse_warp(mods, "iw_kitti_euler_zeros_align", 2, 3, 32, 104, "kitti", "euler", "zeros", seed=16)
+        case_inverse_warp(mods, "iw_large_quat_border_align", 2, 3, 16, 52, "large", "quat", "border", seed=17)
+        case_loss_functions(mods, "lf_images_align", 2, 3, 32, 104, "kitti", seed=18)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("wrote", sorted(os.listdir(OUT)), f"{tot / 1024:.0f} KiB")
 

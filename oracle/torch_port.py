@@ -68,8 +68,9 @@ def pose_matrix(vec, rotation_mode="euler"):
     return torch.cat([R, t], dim=2)
 
 
-def warp(img, depth, pose, K, Kinv, rotation_mode="euler", padding_mode="zeros"):
-    """inverse_warp.py:160-193 (pixel2cam :26-40 and cam2pixel :43-74 inlined, same op order)."""
+def warp(img, depth, pose, K, Kinv, rotation_mode="euler", padding_mode="zeros", align_corners=False):
+    """inverse_warp.py:160-193 (pixel2cam :26-40 and cam2pixel :43-74 inlined, same op order).  align_corners=True is the
+    grid_sample convention of torch <= 1.2, which the reference was written for; today's torch runs it with False."""
     b, h, w = depth.shape
     grid = _pixel_grid(depth)[:, :, :h, :w].expand(b, 3, h, w).reshape(b, 3, -1)
     cam = (Kinv @ grid).reshape(b, 3, h, w) * depth.unsqueeze(1)
@@ -87,6 +88,8 @@ def warp(img, depth, pose, K, Kinv, rotation_mode="euler", padding_mode="zeros")
     coords = torch.stack([Xn, Yn], dim=2).reshape(b, h, w, 2)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")   # the reference does not pass align_corners (-> False + UserWarning)
+        if align_corners:
+            return F.grid_sample(img, coords, padding_mode=padding_mode, align_corners=True)
         return F.grid_sample(img, coords, padding_mode=padding_mode)
 
 

@@ -42,3 +42,23 @@ def ulp_diff(a, b):
     ia = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia)
     ib = np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
     return int(np.abs(ia - ib).max()) if a.size else 0
+
+
+class align_corners:
+    """`with align_corners(ops, name)`: fixtures named *_align come from the reference run with
+    F.grid_sample(align_corners=True) (oracle/gen_golden.py); the binding's module switch selects that convention."""
+
+    def __init__(self, ops, name):
+        self.ops, self.on = ops, str(name).endswith("_align")
+
+    def __enter__(self):
+        self.prev = self.ops.ALIGN_CORNERS
+        self.ops.ALIGN_CORNERS = self.on
+        return self.on
+
+    def __exit__(self, *exc):
+        self.ops.ALIGN_CORNERS = self.prev
+
+
+def oracle_pad(name, pad="zeros"):
+    return pad + ("_align" if str(name).endswith("_align") else "")

@@ -1,0 +1,262 @@
+"""GPU tests of the API surface around the fused kernels: differentiable stand-alone pixel2cam / cam2pixel
+(inverse_warp.py:26-74), descriptor options of ABI v2 (programmatic dependent launch, upstream scalar, sharded means,
+NaN flag), autograd behaviour of the drop-in (retain_graph, two schedules)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import RTOL_F32, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dvf_b200 import ops as _ops, _lib
+    _lib.load()
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def syn():
+    from dvf_b200 import synthetic
+    return synthetic
+
+
+# ---- the reference's two helper functions, restated with the same torch operators (inverse_warp.py:26-40, :43-74) ----
+def ref_pixel2cam(depth, Kinv):
+    b, h, w = depth.size()
+    i_range = torch.arange(0, h).view(1, h, 1).expand(1, h, w).type_as(depth)
+    j_range = torch.arange(0, w).view(1, 1, w).expand(1, h, w).type_as(depth)
+    ones = torch.ones(1, h, w).type_as(depth)
+    pix = torch.stack((j_range, i_range, ones), dim=1).expand(b, 3, h, w).reshape(b, 3, -1)
+    return (Kinv @ pix).reshape(b, 3, h, w) * depth.unsqueeze(1)
+
+
+def ref_cam2pixel(cam, rot, tr, padding_mode):
+    b, _, h, w = cam.size()
+    flat = cam.reshape(b, 3, -1)
+    pc = rot @ flat if rot is not None else flat
+    if tr is not None:
+        pc = pc + tr
+    X, Y, Z = pc[:, 0], pc[:, 1], pc[:, 2].clamp(min=1e-3)
+    Xn = 2 * (X / Z) / (w - 1) - 1
+    Yn = 2 * (Y / Z) / (h - 1) - 1
+    if padding_mode == "zeros":
+        Xm = ((Xn > 1) + (Xn < -1)).detach()
+        Xn[Xm] = 2
+        Ym = ((Yn > 1) + (Yn < -1)).detach()
+        Yn[Ym] = 2
+    return torch.stack([Xn, Yn], dim=2).reshape(b, h, w, 2)
+
+
+def test_pixel2cam_autograd(ops, syn):
+    import inverse_warp as iw
+    B, H, W = 3, 30, 52
+    depth = syn.depth(B, H, W, 5)
+    _, Kinv = syn.intrinsics(B, H, W)
+    gout = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(1))
+    d_ref = depth.clone().requires_grad_(True)
+    c_ref = ref_pixel2cam(d_ref, Kinv)
+    c_ref.backward(gout)
+    d_gpu = depth.cuda().requires_grad_(True)
+    c_gpu = iw.pixel2cam(d_gpu, Kinv.cuda())
+    c_gpu.backward(gout.cuda())
+    assert np.array_equal(npy(c_gpu), c_ref.detach().numpy()), "pixel2cam forward: bit-identical to torch-CPU"
+    assert np.array_equal(npy(d_gpu.grad), d_ref.grad.numpy()), "pixel2cam backward: (g * ray).sum(1) in the same order"
+
+
+@pytest.mark.parametrize("padding", ["zeros", "border"])
+@pytest.mark.parametrize("parts", ["rot+tr", "rot", "tr", "none"])
+def test_cam2pixel_autograd(ops, syn, padding, parts):
+    import inverse_warp as iw
+    B, H, W = 2, 24, 80
+    d = syn.stereo_temporal_batch(B, H, W, seed=11, temporal="large")
+    K, Kinv = d["intrinsics"], d["intrinsics_inv"]
+    cam = ref_pixel2cam(d["depth"], Kinv).detach()
+    from oracle import torch_port as tp
+    P = (K @ tp.pose_matrix(d["T_2to1"])).detach()
+    rot = P[:, :, :3].contiguous() if "rot" in parts else None
+    tr = P[:, :, 3:].contiguous() if "tr" in parts else None
+    if rot is None:   # without a projection the points must already be pixel-like to land inside the image
+        cam = (K @ cam.reshape(B, 3, -1)).reshape(B, 3, H, W).contiguous()
+    gout = torch.randn(B, H, W, 2, generator=torch.Generator().manual_seed(2))
+
+    def run(mod_cam2pixel, dev):
+        c = cam.detach().clone().to(dev).requires_grad_(True)
+        r = None if rot is None else rot.detach().clone().to(dev).requires_grad_(True)
+        t = None if tr is None else tr.detach().clone().to(dev).requires_grad_(True)
+        g = mod_cam2pixel(c, r, t, padding)
+        g.backward(gout.to(dev))
+        return g, c.grad, None if r is None else r.grad, None if t is None else t.grad
+
+    g_ref, gc_ref, gr_ref, gt_ref = run(ref_cam2pixel, "cpu")
+    g_gpu, gc_gpu, gr_gpu, gt_gpu = run(iw.cam2pixel, "cuda")
+    assert np.array_equal(npy(g_gpu), g_ref.detach().numpy()), "cam2pixel forward: bit-identical grid"
+    assert_close(npy(gc_gpu), gc_ref.numpy(), what="d cam_coords")
+    if rot is not None:
+        assert_close(npy(gr_gpu), gr_ref.numpy(), what="d proj_c2p_rot")
+    if tr is not None:
+        assert gt_gpu.shape == tr.shape
+        assert_close(npy(gt_gpu), gt_ref.numpy(), what="d proj_c2p_tr")
+
+
+# ---- descriptor options ----------------------------------------------------------------------------------------------
+def _plans(ops, syn, B, H, W, L, V, n_sets, with_expl=False, **kw):
+    from dvf_b200.plan import FusedLossPlan
+    sizes = [(H >> s, W >> s) for s in range(L)]
+    ds = [float(1 << s) for s in range(L)]
+    out = []
+    for k in range(n_sets):
+        d = syn.stereo_temporal_batch(B, H, W, seed=70 + k)
+        tg = ops.area_pyramid(d["img_R2"].cuda(), sizes)
+        srcs = [ops.area_pyramid(d[n].cuda(), sizes) for n in ("img_R1", "img_L2")][:V]
+        depths = [syn.depth(B, h, w, 80 + 10 * k + i).cuda() for i, (h, w) in enumerate(sizes)]
+        expl = [syn.explainability(B, V, h, w, 90 + i).cuda() for i, (h, w) in enumerate(sizes)] if with_expl else None
+        pose = torch.stack([d["T_2to1"], d["T_R2L"]][:V], 1).contiguous().cuda()
+        out.append(FusedLossPlan(tg, [[sp[l] for sp in srcs] for l in range(L)], depths, pose, d["intrinsics"].cuda(),
+                                 d["intrinsics_inv"].cuda(), expl_levels=expl, downscales=ds, **kw))
+    return out
+
+
+def _snapshot(p):
+    return [npy(p.terms).copy(), npy(p.gpose).copy()] + [npy(g).copy() for g in p.gdepth] + \
+        ([npy(g).copy() for g in p.gexpl] if p.gexpl is not None else [])
+
+
+@pytest.mark.parametrize("V,with_expl", [(1, False), (2, True)])
+def test_pdl_chain_is_bit_identical(ops, syn, V, with_expl):
+    """DVF_FLAG_PDL: back-to-back launches on disjoint buffers overlap; every result equals the plain launch bit for bit,
+    eagerly and replayed from a CUDA graph."""
+    B, H, W, L, S = 6, 64, 208, 3, 3
+    plain = _plans(ops, syn, B, H, W, L, V, S, with_expl)
+    chained = _plans(ops, syn, B, H, W, L, V, S, with_expl, pdl=True)
+    for p in plain:
+        p.launch()
+    torch.cuda.synchronize()
+    want = [_snapshot(p) for p in plain]
+    for _ in range(3):
+        for p in chained:
+            p.launch()
+    torch.cuda.synchronize()
+    for p, w in zip(chained, want):
+        assert all(np.array_equal(a, b) for a, b in zip(_snapshot(p), w)), "PDL launch differs from the plain launch"
+    for p in chained:   # poison the outputs, then replay a captured chain
+        p.terms.fill_(float("nan"))
+        for g in p.gdepth:
+            g.fill_(float("nan"))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(2):
+                for p in chained:
+                    p.launch()
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    g.replay()
+    torch.cuda.synchronize()
+    for p, w in zip(chained, want):
+        assert all(np.array_equal(a, b) for a, b in zip(_snapshot(p), w)), "captured PDL chain differs from the plain launch"
+
+
+def test_upstream_scalar_and_sharded_mean(ops, syn):
+    """dvf_loss_desc.upstream scales every gradient (not the terms); mean_batch makes a shard return its share of the
+    global mean, so that shards add up to the un-sharded call (dvf_b200.dist)."""
+    B, H, W, L, V = 4, 32, 104, 2, 2
+    full = _plans(ops, syn, B, H, W, L, V, 1, True)[0]
+    full.launch()
+    up = torch.tensor([0.25], device="cuda")
+    scaled = _plans(ops, syn, B, H, W, L, V, 1, True, upstream=up)[0]
+    scaled.launch()
+    torch.cuda.synchronize()
+    a, b = _snapshot(full), _snapshot(scaled)
+    assert np.array_equal(a[0], b[0]), "terms are not scaled"
+    for x, y in zip(a[1:], b[1:]):
+        assert_close(y, 0.25 * x, tol=2e-6, what="gradient * upstream")
+    # shards: images [0,2) and [2,4) with mean_batch = 4
+    from dvf_b200.plan import FusedLossPlan
+    tg, srcs, depths, pose, K, Kinv, expl, _ = full.inputs
+    ds = [1.0, 2.0]
+    terms = torch.zeros_like(full.terms)
+    for sl in (slice(0, 2), slice(2, 4)):
+        c = lambda t: t[sl].contiguous()   # noqa: E731
+        p = FusedLossPlan([c(t) for t in tg], [[c(s) for s in lv] for lv in srcs], [c(t) for t in depths], c(pose), c(K), c(Kinv),
+                          expl_levels=[c(t) for t in expl], downscales=ds, global_batch=B)
+        p.launch()
+        torch.cuda.synchronize()
+        terms += p.terms
+        for l in range(L):
+            assert_close(npy(p.gdepth[l]), npy(full.gdepth[l][sl]), tol=1e-6, what="shard gdepth")
+        assert_close(npy(p.gpose), npy(full.gpose[sl]), tol=2e-6, what="shard gpose")
+    assert_close(npy(terms), npy(full.terms), tol=2e-6, what="sum of shard terms")
+
+
+def test_nan_flag(ops, syn):
+    """nan_check=True: the kernel ORs bit l*V+v into ops.nan_flags() when terms[l*V+v] is NaN -- the reference asserts
+    per view and scale with a device sync each (loss_functions_sfm.py:34)."""
+    import loss_functions_sfm as sfm
+    B, H, W = 2, 32, 104
+    d = syn.stereo_temporal_batch(B, H, W, seed=3)
+    t = {k: v.cuda() for k, v in d.items()}
+    depths = [t["depth"].unsqueeze(1), syn.depth(B, H // 2, W // 2, 4).cuda().unsqueeze(1)]
+    pose = torch.stack([t["T_2to1"], t["T_R2L"]], 1)
+    flags = ops.nan_flags()
+    flags.zero_()
+    sfm.NAN_CHECK = True
+    try:
+        sfm.photometric_reconstruction_loss(t["img_R2"], [t["img_R1"], t["img_L2"]], t["intrinsics"], t["intrinsics_inv"], depths,
+                                            [None, None], pose)
+        assert int(flags.item()) == 0
+        bad = [depths[0], depths[1].clone()]
+        bad[1][0, 0, 3, 5] = float("nan")
+        loss = sfm.photometric_reconstruction_loss(t["img_R2"], [t["img_R1"], t["img_L2"]], t["intrinsics"],
+                                                   t["intrinsics_inv"], bad, [None, None], pose)
+        assert torch.isnan(loss).item()
+        assert int(flags.item()) == 0b1100, "level 1, both views"
+        with pytest.raises(AssertionError):
+            sfm.assert_no_nan()
+    finally:
+        sfm.NAN_CHECK = False
+        flags.zero_()
+
+
+def test_retain_graph_and_two_schedules(ops, syn):
+    """backward can run twice (retain_graph=True) for image losses (gradients scaled out of place) and for feature losses
+    (forward-only kernel in forward(), fused pass with the upstream scalar in backward())."""
+    import loss_functions as lf
+    B, H, W = 2, 16, 52
+    for feature, Cc in ((False, 3), (True, 16)):
+        d = syn.stereo_temporal_batch(B, H, W, seed=21, C=Cc, feature=feature)
+        t = {k: v.cuda() for k, v in d.items()}
+        req = ["depth", "T_2to1", "T_R2L"] + (["img_R2", "img_R1", "img_L2"] if feature else [])
+        for k in req:
+            t[k].requires_grad_(True)
+        loss = lf.photometric_reconstruction_loss(t["img_R2"], t["img_R1"], t["img_L2"], t["depth"], t["T_2to1"], t["T_R2L"],
+                                                  t["intrinsics"], t["intrinsics_inv"])
+        (0.1 * loss).backward(retain_graph=True)
+        first = {k: t[k].grad.clone() for k in req}
+        for k in req:
+            t[k].grad = None
+        loss.backward()
+        for k in req:
+            assert_close(npy(first[k]), 0.1 * npy(t[k].grad), tol=RTOL_F32, what=f"{'feature' if feature else 'image'} d {k}")
+
+
+def test_tensors_on_different_devices_are_rejected(ops, syn):
+    from dvf_b200._lib import DvfError
+    d = syn.stereo_temporal_batch(1, 16, 52, seed=1)
+    with pytest.raises(DvfError):
+        import inverse_warp as iw
+        iw.inverse_warp(d["img_R1"], d["depth"].cuda(), d["T_2to1"].cuda(), d["intrinsics"].cuda(), d["intrinsics_inv"].cuda())

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import RTOL_F32, assert_close, golden, golden_names, rel_err, ulp_diff
+from helpers import RTOL_F32, align_corners, assert_close, golden, golden_names, oracle_pad, rel_err, ulp_diff
 
 pytestmark = pytest.mark.gpu
 
@@ -292,6 +292,11 @@ def test_fused_loss_multilevel_matches_per_level(ops, oracle, syn):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", golden_names("iw_"))
 def test_dropin_inverse_warp_golden(ops, name):
+    with align_corners(ops, name):   # *_align fixtures: the torch <= 1.2 sampling convention (DVF_FLAG_ALIGN_CORNERS)
+        _dropin_inverse_warp_golden(ops, name)
+
+
+def _dropin_inverse_warp_golden(ops, name):
     import inverse_warp as iw
     g = golden(name)
     rot, pad = g["rotation_mode"], g["padding_mode"]
@@ -322,6 +327,11 @@ def test_dropin_inverse_warp_golden(ops, name):
 
 @pytest.mark.parametrize("name", golden_names("lf_"))
 def test_dropin_loss_functions_golden(ops, name):
+    with align_corners(ops, name):
+        _dropin_loss_functions_golden(ops, name)
+
+
+def _dropin_loss_functions_golden(ops, name):
     import loss_functions as lf
     g = golden(name)
     feat = "g_img_R1" in g

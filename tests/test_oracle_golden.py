@@ -4,13 +4,13 @@ and validity masks must be bit-identical given the reference's P; gradients with
 import numpy as np
 import pytest
 
-from helpers import assert_close, golden, golden_names, rel_err, ulp_diff
+from helpers import assert_close, golden, golden_names, oracle_pad, rel_err, ulp_diff
 
 
 @pytest.mark.parametrize("name", golden_names("iw_"))
 def test_inverse_warp_golden(oracle, name):
     g = golden(name)
-    rot, pad = g["rotation_mode"], g["padding_mode"]
+    rot, pad = g["rotation_mode"], oracle_pad(name, g["padding_mode"])
     # pose -> P: torch-CPU's sin / cos are restated bit for bit (oracle/torch_trig.h)
     pm = oracle.pose_vec2mat(g["pose"], rot)
     assert np.array_equal(pm, g["posemat"]), "pose_vec2mat must be bit-identical to the reference"
@@ -32,7 +32,7 @@ def test_loss_functions_golden(oracle, name):
     g = golden(name)
     feat = "g_img_R1" in g
     r = oracle.photo_loss_P(g["img_R2"], [g["img_R1"], g["img_L2"]], g["depth"], g["P"], g["intrinsics_inv"],
-                            need_gsrc=feat, need_gtgt=feat)
+                            padding_mode=oracle_pad(name), need_gsrc=feat, need_gtgt=feat)
     assert abs(r["terms"].sum() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
     assert_close(r["gdepth"], g["g_depth"], what="gdepth")
     assert_close(oracle.pose_bwd(r["gP"][:, 0], g["intrinsics"], g["T_2to1"]), g["g_T_2to1"], what="g_T_2to1")

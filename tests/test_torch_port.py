@@ -14,7 +14,7 @@ def test_port_warp_bit_exact(name):
     t = lambda k: torch.from_numpy(g[k])  # noqa: E731
     torch.set_num_threads(1)
     img, depth, pose = t("img").requires_grad_(True), t("depth").requires_grad_(True), t("pose").requires_grad_(True)
-    w = tp.warp(img, depth, pose, t("K"), t("Kinv"), g["rotation_mode"], g["padding_mode"])
+    w = tp.warp(img, depth, pose, t("K"), t("Kinv"), g["rotation_mode"], g["padding_mode"], align_corners=name.endswith("_align"))
     assert np.array_equal(w.detach().numpy(), g["warped"])
     w.backward(t("gout"))
     assert np.array_equal(depth.grad.numpy(), g["gdepth"])
