@@ -181,7 +181,7 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     if (q < d->n_peers && (!prm.peer_terms[q] || !aligned(prm.peer_terms[q], 4))) return DVF_EINVAL_NULL;
   }
   prm.pdl = (d->flags & DVF_FLAG_PDL) ? 1 : 0;
-  if (d->grad_dtype != DVF_F32) return DVF_EUNSUPPORTED;   // TODO bf16 map gradients
+  if (d->grad_dtype != DVF_F32 && !(d->grad_dtype == DVF_BF16 && nhwc && bf16)) return DVF_EUNSUPPORTED;
   prm.grad_bf16 = d->grad_dtype == DVF_BF16;
   bool need_grad = false;
   char* ws = static_cast<char*>(workspace);
@@ -236,7 +236,7 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
   prm.pose_counter = reinterpret_cast<unsigned*>(ws + pl.off_pcnt);
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   if (d->flags & DVF_FLAG_ZERO_GSRC) {
-    const size_t gesz = d->grad_dtype == DVF_BF16 ? 2 : 4;
+    const size_t gesz = 4;   // source-map gradients are fp32
     for (int l = 0; l < d->n_levels; ++l)
       for (int v = 0; v < d->V; ++v)
         if (levels[l].gsrc[v]) {

@@ -9,7 +9,7 @@
 // tap (red.global.add.v4.f32, sm_90+) instead of 4*C scalar atomics per pixel.  The coordinate chain is the
 // scalar exact one (dvf_math.cuh), evaluated once per pixel by an owner lane and broadcast to the group.
 // Arithmetic is fp32 throughout; bf16 inputs are widened on load (geometry stays fp32), gradients to the maps
-// are produced in fp32 NHWC buffers.
+// are produced in fp32 NHWC buffers, or in bf16 ones for bf16 maps when the caller asks for it (grad_dtype).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -90,6 +90,15 @@ __device__ __forceinline__ void red_add_v4(char* base, int byte_off, unsigned pr
       : "memory");
 }
 
+// bf16 target-map gradient (dvf_loss_desc.grad_dtype = DVF_BF16): four channels leave as two packed bf16x2 words.
+// (The source-map gradients stay fp32: they are ACCUMULATED, and bf16x2 reductions -- red.global.add.noftz.v2.bf16x2,
+// tried -- round after every one of the up to 4 contributions of a texel: 1.17e-2 of max|g| on the C4 shape, outside the
+// 1e-2 class of bf16 results.)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 // sums of (x, y[, z]) over aligned groups of kLanes lanes: straight-line xor butterfly (same order as a loop over
 // q = 1, 2, 4, ...: results are bit-identical for every group size)
 template <int kLanes>
@@ -142,6 +151,7 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
   const int ch0 = (lane & (lpp - 1)) * 4;      // first channel of my (first) group of 4; bf16: second group at + C/2
   const unsigned grp_mask = lpp == 32 ? 0xffffffffu : ((1u << lpp) - 1u);
   const bool need_grad = prm.need_grad != 0;
+  const bool grad_bf16 = prm.grad_bf16 != 0;   // target-map gradient in bf16 (bf16 maps only)
 
   // balanced split (same unit list and bookkeeping as the image kernel, dvf_loss_kernel.cuh): this CTA owns units
   // [w, w_end) and walks them (image, level) by (image, level)
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
     gsrc_b[v] = lv.gsrc[v] ? lv.gsrc[v] + img_px * C : nullptr;
     asm volatile("" : "+l"(src_bb[v]), "+l"(gsrc_b[v]));   // keep the bases in registers (nvcc re-derives them per load otherwise)
   }
-  float* gtgt_b = lv.gtgt ? lv.gtgt + img_px * C : nullptr;
+  float* gtgt_b = lv.gtgt ? lv.gtgt + (grad_bf16 ? img_px * C / 2 : img_px * C) : nullptr;
   const char* tgt_bb = tgt_b;
   asm volatile("" : "+l"(tgt_bb), "+l"(gtgt_b));
   const int row_b = W * C * kEsz, px_b = C * kEsz, ch_b = ch0 * kEsz, half_b = (C / 2) * kEsz;   // byte strides of the maps
@@ -354,7 +364,12 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
           if ((lane & (lpp - 1)) == 0) *reinterpret_cast<float4*>(&s_back[warp][v][p][0]) = make_float4(gx, gy, ge, 0.0f);
         }
       }  // views
-      if (need_grad && plive && gtgt_b) {
+      if (kBf16 && grad_bf16 && need_grad && plive && gtgt_b) {
+        char* q = static_cast<char*>(static_cast<void*>(gtgt_b)) + (size_t)pidx * px_b + ch_b;
+#pragma unroll
+        for (int c = 0; c < kVec; c += 4)
+          *reinterpret_cast<uint2*>(q + (c / 4) * half_b) = make_uint2(pack_bf16x2(gt[c], gt[c + 1]), pack_bf16x2(gt[c + 2], gt[c + 3]));
+      } else if (need_grad && plive && gtgt_b) {
         float* q = gtgt_b + (size_t)pidx * C + ch0;
 #pragma unroll
         for (int c = 0; c < kVec; c += 4)

@@ -485,6 +485,10 @@ class _LossCall:
             terms = torch.empty(L * V, device=dev, dtype=torch.float32)
             levels = (dvf_level * L)()
             g_tgt, g_src, g_depth, g_expl = [None] * L, [None] * (L * V), [None] * L, [None] * L
+            # channels-last bf16 maps get their target-map gradient in bf16 straight from the kernel (source-map gradients are
+            # accumulated in fp32 and converted below)
+            bf16_grads = self.layout == _lib.NHWC and self.dtype == _lib.BF16
+            gdt = torch.bfloat16 if bf16_grads else torch.float32
             for l in range(L):
                 lv = levels[l]
                 h, w = self.depths[l].shape[1], self.depths[l].shape[2]
@@ -494,7 +498,7 @@ class _LossCall:
                     sv = self.srcs[l * V + v]
                     lv.src[v] = sv.data_ptr()
                     if want_grads and self.need_src[l * V + v]:
-                        g_src[l * V + v] = torch.empty_like(sv, dtype=torch.float32)   # zero-filled by the entry (DVF_FLAG_ZERO_GSRC)
+                        g_src[l * V + v] = torch.empty_like(sv, dtype=torch.float32)   # accumulated in fp32; zero-filled by the entry
                         lv.gsrc[v] = g_src[l * V + v].data_ptr()
                 if cfg.has_expl:
                     e = self.expls[l]
@@ -507,14 +511,14 @@ class _LossCall:
                     g_depth[l] = torch.empty_like(self.depths[l])
                     lv.gdepth = g_depth[l].data_ptr()
                 if want_grads and self.need_tgt[l]:
-                    g_tgt[l] = torch.empty_like(self.tgts[l], dtype=torch.float32)
+                    g_tgt[l] = torch.empty_like(self.tgts[l], dtype=gdt)
                     lv.gtgt = g_tgt[l].data_ptr()
             flags = _flags(cfg.align_corners) | _lib.FLAG_ZERO_GSRC | (_lib.FLAG_NAN_CHECK if cfg.nan_check else 0)
             up = None
             if upstream is not None:
                 up = upstream.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
             d = dvf_loss_desc(B, Cc, V, L, self.dtype, self.layout, PADDING[cfg.padding_mode], flags,
-                              int(cfg.global_batch or 0), _lib.F32, 0, 0, _ptr(up),
+                              int(cfg.global_batch or 0), _lib.BF16 if bf16_grads else _lib.F32, 0, 0, _ptr(up),
                               nan_flags(dev).data_ptr() if cfg.nan_check else None, 0, 0, None)
             nbytes = lib.dvf_photo_loss_workspace_bytes(C.byref(d), levels)
             if nbytes == 0:

@@ -27,7 +27,7 @@ class FusedLossPlan:
                  map_grads: bool = False, global_batch: Optional[int] = None, align_corners: bool = False,
                  upstream: Optional[torch.Tensor] = None, fused_pose: bool = True, use_tma: bool = True,
                  piece_overhead: int = 0, ctas_per_sm: int = 0, pdl: bool = False,
-                 peer_terms: Optional[Sequence[int]] = None, peer_rank: int = 0):
+                 peer_terms: Optional[Sequence[int]] = None, peer_rank: int = 0, bf16_grads: bool = True):
         """Maps: dense NCHW fp32 (images, any C) or channels-last fp32 / bf16 feature maps ([B,C,H,W] tensors in
         torch.channels_last memory).  map_grads: also produce d/d tgt and d/d src (fp32, layout of the maps).
         global_batch: this plan holds B of the global_batch images of a sharded batch (dvf_loss_desc.mean_batch).
@@ -66,7 +66,9 @@ class FusedLossPlan:
         self.gexpl = ([torch.empty(B, V, e.shape[2], e.shape[3], device=dev) for e in expl_levels]
                       if (need_grad and expl_levels is not None) else None)
         self.map_grads = bool(map_grads and need_grad)
-        self.gtgt = [torch.empty_like(t, dtype=torch.float32) for t in tgt_levels] if self.map_grads else None
+        self.grad_bf16 = bool(bf16_grads) and layout == _lib.NHWC and dtype == _lib.BF16
+        gdt = torch.bfloat16 if self.grad_bf16 else torch.float32
+        self.gtgt = [torch.empty_like(t, dtype=gdt) for t in tgt_levels] if self.map_grads else None
         self.gsrc = ([[torch.empty_like(t, dtype=torch.float32) for t in lv] for lv in src_levels]
                      if self.map_grads else None)   # zero-filled by the entry on every launch (DVF_FLAG_ZERO_GSRC)
         self.levels = (dvf_level * L)()
@@ -90,7 +92,7 @@ class FusedLossPlan:
                         lv.gsrc[v] = self.gsrc[l][v].data_ptr()
         flags = (_lib.FLAG_ALIGN_CORNERS if align_corners else 0) | (_lib.FLAG_ZERO_GSRC if self.map_grads else 0) | \
                 (0 if use_tma else _lib.FLAG_NO_TMA) | (_lib.FLAG_PDL if pdl else 0)
-        self.desc = dvf_loss_desc(B, Cc, V, L, dtype, layout, PADDING[padding_mode], flags, int(global_batch or 0), _lib.F32,
+        self.desc = dvf_loss_desc(B, Cc, V, L, dtype, layout, PADDING[padding_mode], flags, int(global_batch or 0), _lib.BF16 if self.grad_bf16 else _lib.F32,
                                   int(piece_overhead), int(ctas_per_sm), None if upstream is None else upstream.data_ptr(), None,
                                   0, 0, None)
         if peer_terms:
@@ -163,8 +165,8 @@ class FusedLossPlan:
         per_tpx = 4 + self.C * e + g                                      # depth + target (+ d depth), once per target pixel
         per_wpx = self.C * e                                              # source texels, once per warped pixel
         if self.map_grads:
-            per_tpx += self.C * 4                                         # d target (fp32), written once
-            per_wpx += self.C * 4                                         # d source (fp32), one write per texel
+            per_tpx += self.C * (2 if self.grad_bf16 else 4)              # d target, written once
+            per_wpx += self.C * 4                                         # d source (fp32, accumulated), one write per texel
         if self.inputs[6] is not None:
             per_wpx += 4 + g                                              # explainability read (+ its gradient)
         tpx = self.warped_px // self.V

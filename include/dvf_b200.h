@@ -169,8 +169,8 @@ typedef struct dvf_level {
   const float* Kinv;                /* [B,3,3]                                */
   float* gdepth;                    /* [B,H,W] written                        */
   float* gexpl;                     /* [B,V,H,W] dense, written               */
-  void* gsrc[DVF_MAX_VIEWS];        /* grad_dtype, layout of src; ACCUMULATED (see DVF_FLAG_ZERO_GSRC) */
-  void* gtgt;                       /* grad_dtype, layout of tgt; written     */
+  void* gsrc[DVF_MAX_VIEWS];        /* fp32, layout of src; ACCUMULATED (see DVF_FLAG_ZERO_GSRC) */
+  void* gtgt;                       /* dvf_loss_desc.grad_dtype, layout of tgt; written */
   float* gP;                        /* [B,V,3,4] written                      */
 } dvf_level;
 
@@ -181,7 +181,8 @@ typedef struct dvf_loss_desc {
   int32_t mean_batch;     /* batch size in the denominator of the means; 0 = B.  A rank that holds B
                              of the mean_batch images of a sharded batch passes the global size and
                              gets its share of the global loss and gradients (no collective needed) */
-  int32_t grad_dtype;     /* dvf_dtype of gsrc / gtgt: DVF_F32, or DVF_BF16 for NHWC bf16 maps      */
+  int32_t grad_dtype;     /* dvf_dtype of gtgt: DVF_F32, or DVF_BF16 for NHWC bf16 maps (gsrc is accumulated
+                             and therefore always fp32)                                            */
   int32_t piece_overhead; /* tuning: fixed cost of an (image, level) piece in 256-px units; <= 0 = default */
   int32_t ctas_per_sm;    /* tuning: resident CTAs per SM of the image kernel's grid; <= 0 = occupancy query */
   const float* upstream;  /* device scalar g = d(total)/d(sum of terms): every gradient is scaled by it
