@@ -453,9 +453,14 @@ def timed(runner, n, world, dev):
     return float(ms.item())
 
 
+LOSS_KERNEL_SOURCES = ("dvf_loss*", "dvf_math*", "dvf_tma.cuh", "dvf_reduce.cuh", "dvf_pose.cuh", "dvf_internal.h")
+
+
 def csrc_sha16():
+    """hash of the sources the fused loss kernels are built from: profiles/traffic.json records it at capture time"""
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(PKG, "csrc", "*"))):
+    files = sorted({f for pat in LOSS_KERNEL_SOURCES for f in glob.glob(os.path.join(PKG, "csrc", pat))})
+    for f in files:
         h.update(open(f, "rb").read())
     return h.hexdigest()[:16]
 

@@ -240,6 +240,86 @@ __global__ void __launch_bounds__(kThreads) caffe_abs_loss_kernel(const float* _
 }
 __global__ void caffe_abs_loss_finish(const double* acc, int num, float* out) { *out = (float)(*acc / (double)num); }
 
+
+// ---- edge-aware smoothness of the Caffe graphs (experiments/depth/train.prototxt:4022-4234) ------------------------------
+// The prototxt spells it with ten layers: 3x3 "EdgeX" / "EdgeY" convolutions without padding (caffe/include/caffe/filler.hpp:
+// 266-315: EdgeX = half the difference between the row below and the row above, EdgeY = half the difference between the
+// right and the left column), AbsVal, a 1x1 convolution with weights -0.33 over the three colour channels, Exp, the same
+// two edge convolutions on the inverse depth, Eltwise PROD, and AbsLoss against zeros with loss_weight 10:
+//   gx(i,j) = exp(-0.33 * sum_c |EdgeX(I_c)(i,j)|),   dx = gx * EdgeX(D),   loss_x = sum |dx| / N      (same with y)
+// over the (H-2) x (W-2) window origins.  One launch computes both loss terms and d(w*loss_x + w*loss_y)/dD; the image is
+// data (lr_mult 0 convolutions on an input blob).  Gather form of the gradient: D(r,c) is the lower operand of window
+// (r-2,c-1), the upper one of (r,c-1), the right one of (r-1,c-2) and the left one of (r-1,c).
+struct EdgeWin {
+  float gx, gy, dx, dy;
+};
+__device__ __forceinline__ EdgeWin edge_window(const float* __restrict__ img, const float* __restrict__ D, int HW, int W, int i, int j) {
+  // window origin (i, j): rows i..i+2, columns j..j+2
+  const int up = i * W + j + 1, dn = (i + 2) * W + j + 1, lf = (i + 1) * W + j, rt = (i + 1) * W + j + 2;
+  float sx = 0.0f, sy = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* p = img + (size_t)c * HW;
+    sx = add(sx, fabsf(mul(0.5f, sub(__ldg(p + dn), __ldg(p + up)))));
+    sy = add(sy, fabsf(mul(0.5f, sub(__ldg(p + rt), __ldg(p + lf)))));
+  }
+  EdgeWin w;
+  w.gx = expf(mul(-0.33f, sx));
+  w.gy = expf(mul(-0.33f, sy));
+  w.dx = mul(w.gx, mul(0.5f, sub(__ldg(D + dn), __ldg(D + up))));
+  w.dy = mul(w.gy, mul(0.5f, sub(__ldg(D + rt), __ldg(D + lf))));
+  return w;
+}
+// d|v|/dv of AbsLoss's second bottom: +1 for v >= 0, -1 for v < 0 (abs_loss_layer.cu:27-29 with diff = 0 - v), 0 for NaN
+__device__ __forceinline__ float abs_loss_sign(float v) { return v != v ? 0.0f : (v >= 0.0f ? 1.0f : -1.0f); }
+
+__global__ void __launch_bounds__(kThreads) caffe_edge_smooth_kernel(const float* __restrict__ img, const float* __restrict__ invd, int H,
+                                                                    int W, float alpha /* loss_weight / N */, float* __restrict__ ginv,
+                                                                    double* __restrict__ acc /*[2]*/) {
+  const int n = blockIdx.y, HW = H * W;
+  const int idx = blockIdx.x * kThreads + threadIdx.x;
+  const float* I = img + (size_t)n * 3 * HW;
+  const float* D = invd + (size_t)n * HW;
+  double lx = 0.0, ly = 0.0;
+  if (idx < HW) {
+    const int r = idx / W, c = idx - r * W;
+    auto valid = [&](int i, int j) { return i >= 0 && j >= 0 && i < H - 2 && j < W - 2; };
+    if (valid(r, c)) {
+      const EdgeWin w = edge_window(I, D, HW, W, r, c);
+      lx = fabs((double)w.dx);
+      ly = fabs((double)w.dy);
+    }
+    if (ginv) {
+      float g = 0.0f;
+      if (valid(r - 2, c - 1)) { const EdgeWin w = edge_window(I, D, HW, W, r - 2, c - 1); g = add(g, mul(0.5f, mul(mul(alpha, abs_loss_sign(w.dx)), w.gx))); }
+      if (valid(r, c - 1)) { const EdgeWin w = edge_window(I, D, HW, W, r, c - 1); g = sub(g, mul(0.5f, mul(mul(alpha, abs_loss_sign(w.dx)), w.gx))); }
+      if (valid(r - 1, c - 2)) { const EdgeWin w = edge_window(I, D, HW, W, r - 1, c - 2); g = add(g, mul(0.5f, mul(mul(alpha, abs_loss_sign(w.dy)), w.gy))); }
+      if (valid(r - 1, c)) { const EdgeWin w = edge_window(I, D, HW, W, r - 1, c); g = sub(g, mul(0.5f, mul(mul(alpha, abs_loss_sign(w.dy)), w.gy))); }
+      ginv[(size_t)n * HW + idx] = g;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lx += __shfl_xor_sync(0xffffffffu, lx, o);
+    ly += __shfl_xor_sync(0xffffffffu, ly, o);
+  }
+  __shared__ double s[2][kThreads / 32];
+  if ((threadIdx.x & 31) == 0) {
+    s[0][threadIdx.x >> 5] = lx;
+    s[1][threadIdx.x >> 5] = ly;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += s[threadIdx.x][w];
+    atomicAdd(acc + threadIdx.x, t);
+  }
+}
+__global__ void caffe_edge_smooth_finish(const double* acc, int num, float* out) {
+  out[0] = (float)(acc[0] / (double)num);
+  out[1] = (float)(acc[1] / (double)num);
+}
+
 static bool bad_nhw(int N, int H, int W) { return N <= 0 || H <= 0 || W <= 0 || N > 65535 || (long long)H * W >= (1ll << 30); }
 static dim3 grid_of(int N, int HW) { return dim3((HW + kThreads - 1) / kThreads, N); }
 
@@ -319,5 +399,18 @@ DVF_EXPORT int dvf_caffe_abs_loss(const float* a, const float* b, uint64_t count
   if (blocks > cap) blocks = cap;
   caffe_abs_loss_kernel<<<(unsigned)blocks, kThreads, 0, cs>>>(a, b, (size_t)count, weight / (float)num, ga, gb, acc);
   caffe_abs_loss_finish<<<1, 1, 0, cs>>>(acc, num, loss);
+  return launch_status();
+}
+
+DVF_EXPORT int dvf_caffe_edge_smooth_loss(const float* img, const float* inv_depth, int32_t N, int32_t H, int32_t W, float weight,
+                                          float* loss, float* ginv, void* workspace, void* stream) {
+  if (!img || !inv_depth || !loss || !workspace) return DVF_EINVAL_NULL;
+  if (bad_nhw(N, H, W) || H < 3 || W < 3) return DVF_EINVAL_SHAPE;
+  if (!aligned(workspace, 8)) return DVF_EINVAL_ALIGN;
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  double* acc = static_cast<double*>(workspace);
+  cudaMemsetAsync(acc, 0, 2 * sizeof(double), cs);
+  caffe_edge_smooth_kernel<<<grid_of(N, H * W), kThreads, 0, cs>>>(img, inv_depth, H, W, weight / (float)N, ginv, acc);
+  caffe_edge_smooth_finish<<<1, 1, 0, cs>>>(acc, N, loss);
   return launch_status();
 }

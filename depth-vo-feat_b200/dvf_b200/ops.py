@@ -821,3 +821,37 @@ class AbsLoss(torch.autograd.Function):
         ga = saved.pop(0) * g if ctx.has[0] else None
         gb = saved.pop(0) * g if ctx.has[1] else None
         return ga, gb
+
+
+class EdgeAwareSmoothness(torch.autograd.Function):
+    """Edge-aware smoothness of the Caffe training graphs (experiments/depth/train.prototxt:4022-4234: EdgeX / EdgeY
+    convolutions, AbsVal, -0.33 1x1 convolution, Exp, Eltwise PROD, AbsLoss with loss_weight): returns
+    weight * (sum|gx * dx(inv_depth)| + sum|gy * dy(inv_depth)|) / N with gx = exp(-0.33 * sum_c |dx(img_c)|); one launch for
+    the value and d/d inv_depth.  img [N,3,H,W] is data, inv_depth [N,1,H,W]."""
+
+    @staticmethod
+    def forward(ctx, img, inv_depth, weight):
+        lib = _lib.load()
+        I, D = _req(img, "img", 4), _req(inv_depth, "inv_depth", 4)
+        N, three, H, W = I.shape
+        if three != 3 or tuple(D.shape) != (N, 1, H, W):
+            raise AssertionError(f"wrong sizes, expected img [N,3,H,W] and inv_depth [N,1,H,W], got {list(I.shape)} and {list(D.shape)}")
+        if ctx.needs_input_grad[0]:
+            raise DvfError("the image is data in the reference graph (lr_mult 0 edge convolutions): no gradient w.r.t. img")
+        terms = torch.empty(2, device=I.device, dtype=torch.float32)
+        g = torch.empty_like(D) if ctx.needs_input_grad[1] else None
+        ws = workspace(16, I.device, ("edge_smooth",))
+        with _same_device(I, D):
+            _lib.check(lib.dvf_caffe_edge_smooth_loss(_ptr(I), _ptr(D), N, H, W, float(weight), _ptr(terms), _ptr(g), _ptr(ws),
+                                                      _stream()), "dvf_caffe_edge_smooth_loss")
+        ctx.unit_grad = g
+        return terms.sum() * float(weight)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        return None, (None if ctx.unit_grad is None else ctx.unit_grad * gout), None
+
+
+def edge_aware_smoothness(img, inv_depth, weight=10.0):
+    return EdgeAwareSmoothness.apply(img, inv_depth, weight)

@@ -287,6 +287,14 @@ int dvf_caffe_warp_bwd(const float* top_diff, const float* img, const float* coo
 int dvf_caffe_abs_loss(const float* a, const float* b, uint64_t count, int32_t num, float weight, float* loss, float* ga,
                        float* gb, void* workspace, void* stream);
 
+/* Edge-aware smoothness of the Caffe graphs (experiments/depth/train.prototxt:4022-4234, fillers caffe/include/caffe/
+ * filler.hpp:266-315): gx = exp(-0.33 * sum_c |EdgeX(img_c)|), dx = gx * EdgeX(inv_depth) over the (H-2)x(W-2) valid
+ * window origins, likewise y; loss[0] = sum|dx| / N, loss[1] = sum|dy| / N (the two AbsLoss tops, un-weighted);
+ * ginv [N,1,H,W] (nullable) = d(weight * (loss[0] + loss[1])) / d inv_depth (the prototxt uses loss_weight 10 for both).
+ * img [N,3,H,W], inv_depth [N,1,H,W]; workspace: >= 16 bytes, 8-aligned.                                        */
+int dvf_caffe_edge_smooth_loss(const float* img, const float* inv_depth, int32_t N, int32_t H, int32_t W, float weight,
+                               float* loss /*[2]*/, float* ginv, void* workspace, void* stream);
+
 /* ---- torch.sin / torch.cos of fp32 values exactly as torch-CPU evaluates them ------------------
  * (reference: inverse_warp.py:89-91,98-99,105-106 -- euler2mat's torch.cos / torch.sin, which on the
  * CPU run MKL's VML in high-accuracy mode).  Bit-identical to torch 2.11 CPU for |x| <= 10000; larger

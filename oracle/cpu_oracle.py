@@ -268,3 +268,13 @@ def caffe_abs_loss(a, b, weight=1.0):
     f.restype = C.c_double
     val = f(_p(a), _p(b), C.c_size_t(a.size), a.shape[0], C.c_float(weight), _p(ga), _p(gb))
     return val, ga, gb
+
+
+def caffe_edge_smooth(img, inv_depth, weight=10.0, need_grad=True):
+    """(loss[2] float64, ginv) of the Caffe graphs' edge-aware smoothness (PARITY UNPINNED, see dvf_oracle.c)."""
+    img, inv_depth = _f32(img), _f32(inv_depth)
+    N, _, H, W = img.shape
+    loss = np.zeros(2, np.float64)
+    g = np.empty((N, 1, H, W), np.float32) if need_grad else None
+    lib().dvfo_caffe_edge_smooth(_p(img), _p(inv_depth), N, H, W, C.c_float(weight), loss.ctypes.data_as(C.c_void_p), _p(g))
+    return loss, g

@@ -911,3 +911,53 @@ DVFO_API double dvfo_caffe_abs_loss(const float *a, const float *b, size_t count
   }
   return s / (double)num;
 }
+
+/* Edge-aware smoothness of the Caffe graphs (experiments/depth/train.prototxt:4022-4234; EdgeX / EdgeY fillers
+ * caffe/include/caffe/filler.hpp:266-315; AbsLoss caffe/src/caffe/layers/abs_loss_layer.cu:10-50).  PARITY UNPINNED like the
+ * other Caffe-convention blocks (BVLC Caffe is not buildable here): the layer chain is restated operator by operator on
+ * materialised blobs -- convolution without padding, AbsVal, 1x1 convolution with -0.33, Exp, Eltwise PROD, AbsLoss against
+ * zeros -- and back-propagated layer by layer (scatter form), so that the CUDA kernel's fused gather form is checked against
+ * an independently structured computation.  loss[0..1] un-weighted, ginv = d(weight*(loss0+loss1))/d inv_depth. */
+DVFO_API void dvfo_caffe_edge_smooth(const float *img, const float *invd, int N, int H, int W, float weight, double *loss,
+                                     float *ginv) {
+  const int h = H - 2, w = W - 2, HW = H * W;
+  float *gx = (float *)malloc(sizeof(float) * h * w), *gy = (float *)malloc(sizeof(float) * h * w);
+  float *ex = (float *)malloc(sizeof(float) * h * w), *ey = (float *)malloc(sizeof(float) * h * w);
+  double lx = 0.0, ly = 0.0;
+  if (ginv) memset(ginv, 0, sizeof(float) * (size_t)N * HW);
+  for (int n = 0; n < N; ++n) {
+    const float *I = img + (size_t)n * 3 * HW, *D = invd + (size_t)n * HW;
+    for (int i = 0; i < h; ++i)
+      for (int j = 0; j < w; ++j) {
+        float sx = 0.0f, sy = 0.0f;
+        for (int c = 0; c < 3; ++c) {
+          const float *p = I + (size_t)c * HW;
+          sx = sx + fabsf(0.5f * (p[(i + 2) * W + j + 1] - p[i * W + j + 1]));   /* EdgeX: rows below - above */
+          sy = sy + fabsf(0.5f * (p[(i + 1) * W + j + 2] - p[(i + 1) * W + j])); /* EdgeY: columns right - left */
+        }
+        gx[i * w + j] = expf(-0.33f * sx);
+        gy[i * w + j] = expf(-0.33f * sy);
+        ex[i * w + j] = gx[i * w + j] * (0.5f * (D[(i + 2) * W + j + 1] - D[i * W + j + 1]));
+        ey[i * w + j] = gy[i * w + j] * (0.5f * (D[(i + 1) * W + j + 2] - D[(i + 1) * W + j]));
+        lx += fabs((double)ex[i * w + j]);
+        ly += fabs((double)ey[i * w + j]);
+      }
+    if (ginv) {
+      float *G = ginv + (size_t)n * HW;
+      const float alpha = weight / (float)N;
+      for (int i = 0; i < h; ++i)
+        for (int j = 0; j < w; ++j) {
+          const float vx = ex[i * w + j], vy = ey[i * w + j];
+          const float sx = vx != vx ? 0.0f : (vx >= 0.0f ? 1.0f : -1.0f), sy = vy != vy ? 0.0f : (vy >= 0.0f ? 1.0f : -1.0f);
+          const float tx = 0.5f * ((alpha * sx) * gx[i * w + j]), ty = 0.5f * ((alpha * sy) * gy[i * w + j]);
+          G[(i + 2) * W + j + 1] += tx;
+          G[i * W + j + 1] -= tx;
+          G[(i + 1) * W + j + 2] += ty;
+          G[(i + 1) * W + j] -= ty;
+        }
+    }
+  }
+  loss[0] = lx / (double)N;
+  loss[1] = ly / (double)N;
+  free(gx); free(gy); free(ex); free(ey);
+}

@@ -88,3 +88,39 @@ def test_closed_forms(oracle):
     assert val == 0.0 and np.all(ga == np.float32(-1.0 / N)) and np.all(gb == np.float32(1.0 / N))
     val, ga, _ = oracle.caffe_abs_loss(img + 1.0, img)
     assert abs(val - img.size / N) < 1e-3 and np.all(ga == np.float32(1.0 / N))
+
+
+def test_edge_aware_smoothness_oracle(oracle):
+    """Caffe edge-aware smoothness (experiments/depth/train.prototxt:4022-4234), PARITY UNPINNED: closed forms and central
+    finite differences of the oracle's own forward."""
+    rng = np.random.default_rng(5)
+    N, H, W = 2, 9, 11
+    img = rng.random((N, 3, H, W), dtype=np.float32)
+    inv = (rng.random((N, 1, H, W), dtype=np.float32) * 0.3 + 0.02).astype(np.float32)
+    loss, g = oracle.caffe_edge_smooth(img, inv, weight=10.0)
+    # flat image -> gx = gy = 1: plain sums of |central differences| over the valid windows
+    l0, _ = oracle.caffe_edge_smooth(np.full_like(img, 0.5), inv, need_grad=False)
+    D = inv[:, 0].astype(np.float64)
+    dx = 0.5 * (D[:, 2:, 1:-1] - D[:, :-2, 1:-1])
+    dy = 0.5 * (D[:, 1:-1, 2:] - D[:, 1:-1, :-2])
+    assert abs(l0[0] - np.abs(dx).sum() / N) < 1e-6 and abs(l0[1] - np.abs(dy).sum() / N) < 1e-6
+    # ramp in x only: EdgeX (vertical difference) vanishes, EdgeY is the slope
+    ramp = np.tile(np.arange(W, dtype=np.float32) * 0.01, (N, 1, H, 1))
+    lr, _ = oracle.caffe_edge_smooth(np.full_like(img, 0.5), ramp, need_grad=False)
+    assert lr[0] == 0.0 and abs(lr[1] - (H - 2) * (W - 2) * 0.01) < 1e-6
+    # finite differences (fp64 restatement of the forward)
+    def f64(inv64):
+        I = img.astype(np.float64)
+        sx = np.abs(0.5 * (I[:, :, 2:, 1:-1] - I[:, :, :-2, 1:-1])).sum(1)
+        sy = np.abs(0.5 * (I[:, :, 1:-1, 2:] - I[:, :, 1:-1, :-2])).sum(1)
+        d = inv64[:, 0]
+        ex = np.exp(-0.33 * sx) * 0.5 * (d[:, 2:, 1:-1] - d[:, :-2, 1:-1])
+        ey = np.exp(-0.33 * sy) * 0.5 * (d[:, 1:-1, 2:] - d[:, 1:-1, :-2])
+        return 10.0 * (np.abs(ex).sum() + np.abs(ey).sum()) / N
+    assert abs(f64(inv.astype(np.float64)) - 10.0 * loss.sum()) < 1e-5 * 10.0 * loss.sum()
+    eps = 1e-6
+    for (n, r, c) in [(0, 0, 1), (0, 4, 5), (1, 8, 9), (1, 3, 0), (0, 2, 10)]:
+        a = inv.astype(np.float64); b = a.copy()
+        a[n, 0, r, c] += eps; b[n, 0, r, c] -= eps
+        fd = (f64(a) - f64(b)) / (2 * eps)
+        assert abs(fd - g[n, 0, r, c]) < 1e-4 * max(1.0, abs(fd)), (n, r, c, fd, g[n, 0, r, c])

@@ -876,3 +876,19 @@ def test_regularisers_dropins_vs_reference_golden(ops):
     assert abs(ev.item() - float(g["expl"])) <= RTOL_F32 * float(g["expl"])
     for i, x in enumerate(tm):
         assert_close(npy(x.grad), g[f"g_mask{i}"], what=f"expl grad {i}")
+
+
+def test_caffe_edge_aware_smoothness_vs_oracle(ops, oracle):
+    """Caffe graphs' edge-aware smoothness (experiments/depth/train.prototxt:4022-4234; parity unpinned): the fused gather
+    kernel against the oracle's layer-by-layer scatter form, value and gradient."""
+    rng = np.random.default_rng(9)
+    for (N, H, W) in [(2, 9, 11), (3, 40, 64), (1, 3, 3), (2, 160, 608)]:
+        img = rng.random((N, 3, H, W), dtype=np.float32)
+        inv = (rng.random((N, 1, H, W), dtype=np.float32) * 0.3 + 0.02).astype(np.float32)
+        inv[0, 0, H // 2, :] = inv[0, 0, H // 2, 0]          # exact zeros in dy: AbsLoss's sign(0) = +1
+        loss, g = oracle.caffe_edge_smooth(img, inv, weight=10.0)
+        d = cu(inv).requires_grad_(True)
+        out = ops.edge_aware_smoothness(cu(img), d, 10.0)
+        out.backward()
+        assert abs(out.item() - 10.0 * loss.sum()) <= 2e-6 * 10.0 * loss.sum()
+        assert_close(npy(d.grad), g, tol=2e-6, what=f"d inv_depth {N}x{H}x{W}")
