@@ -92,6 +92,7 @@ SIGNATURES = {
     "dvf_caffe_warp_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "dvf_caffe_abs_loss": (C.c_int, [_vp, _vp, C.c_uint64, _i32, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     "dvf_caffe_edge_smooth_loss": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.c_float, _vp, _vp, _vp, _vp]),
+    "dvf_ssim_loss": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "dvf_torch_sincos": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp]),
     "dvf_selftest_fast_div": (C.c_int, [C.c_uint64, C.c_uint64, _i32, _vp, _vp]),
 }

@@ -855,3 +855,41 @@ class EdgeAwareSmoothness(torch.autograd.Function):
 
 def edge_aware_smoothness(img, inv_depth, weight=10.0):
     return EdgeAwareSmoothness.apply(img, inv_depth, weight)
+
+
+class SSIMLoss(torch.autograd.Function):
+    """SSIM reconstruction term (csrc/dvf_ssim.cu; NOT in the reference -- new functionality, parity unpinned): 3x3
+    average-pool SSIM, loss = mean over windows of clamp((1 - SSIM(x, y)) / 2, 0, 1), windows that touch an invalid pixel
+    contribute zero.  x = target (data), y = warped image (differentiable), valid = uint8 [B,H,W] or None."""
+
+    @staticmethod
+    def forward(ctx, x, y, valid):
+        lib = _lib.load()
+        xs, ys = _req(x, "x", 4), _req(y, "y", 4)
+        if xs.shape != ys.shape:
+            raise AssertionError(f"wrong size for y, expected {list(xs.size())}, got {list(ys.size())}")
+        if ctx.needs_input_grad[0]:
+            raise DvfError("ssim_loss differentiates w.r.t. its second argument (the warped image) only")
+        B, Cc, H, W = xs.shape
+        v = None
+        if valid is not None:
+            if valid.dtype != torch.uint8 or tuple(valid.shape) != (B, H, W) or not valid.is_cuda:
+                raise AssertionError(f"wrong valid mask, expected uint8 CUDA [B,H,W], got {valid.dtype} {list(valid.size())}")
+            v = valid.contiguous()
+        loss = torch.empty(1, device=xs.device, dtype=torch.float32)
+        gy = torch.empty_like(ys) if ctx.needs_input_grad[1] else None
+        ws = workspace(8, xs.device, ("ssim",))
+        with _same_device(xs, ys, v):
+            _lib.check(lib.dvf_ssim_loss(_ptr(xs), _ptr(ys), _ptr(v), B, Cc, H, W, _ptr(loss), _ptr(gy), _ptr(ws), _stream()),
+                       "dvf_ssim_loss")
+        ctx.unit_grad = gy
+        return loss[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        return None, (None if ctx.unit_grad is None else ctx.unit_grad * gout), None
+
+
+def ssim_loss(x, y, valid=None):
+    return SSIMLoss.apply(x, y, valid)

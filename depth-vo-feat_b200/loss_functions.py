@@ -32,3 +32,20 @@ def inverse_warp(img, depth, pose, intrinsics, intrinsics_inv, rotation_mode='eu
     """The copy embedded in loss_functions.py:198-231 has the 'B3HW' check disabled (:211)."""
     return _inverse_warp_checked(img, depth, pose, intrinsics, intrinsics_inv, rotation_mode, padding_mode,
                                  check_channels=False)
+
+
+def photometric_ssim_reconstruction_loss(img_R2, img_R1, img_L2, depth, T_2to1, T_R2L, intrinsics, intrinsics_inv,
+                                         rotation_mode='euler', padding_mode='zeros', alpha=0.85):
+    """NOT in the reference (it has no SSIM term; BASELINE's north_star names "masked photometric (L1/SSIM)"): the usual
+    monocular-depth mix  (1 - alpha) * L1 + alpha * SSIM  over the same two views and the same validity masks as
+    photometric_reconstruction_loss above.  The L1 part is the fused launch; the SSIM part warps each source image
+    (dvf_inverse_warp_fwd, which also yields the mask), evaluates dvf_ssim_loss (value + d/d warped in one launch) and
+    back-propagates through dvf_inverse_warp_bwd.  Parity unpinned (csrc/dvf_ssim.cu states the definition)."""
+    l1 = photometric_reconstruction_loss(img_R2, img_R1, img_L2, depth, T_2to1, T_R2L, intrinsics, intrinsics_inv,
+                                         rotation_mode, padding_mode)
+    ssim = 0
+    for src, pose in ((img_R1, T_2to1), (img_L2, T_R2L)):
+        warped = inverse_warp(src, depth, pose, intrinsics, intrinsics_inv, rotation_mode, padding_mode)
+        valid = (warped.detach() != 0).any(1).to(torch.uint8)
+        ssim = ssim + _ops.ssim_loss(img_R2, warped, valid)
+    return (1.0 - alpha) * l1 + alpha * ssim

@@ -295,6 +295,15 @@ int dvf_caffe_abs_loss(const float* a, const float* b, uint64_t count, int32_t n
 int dvf_caffe_edge_smooth_loss(const float* img, const float* inv_depth, int32_t N, int32_t H, int32_t W, float weight,
                                float* loss /*[2]*/, float* ginv, void* workspace, void* stream);
 
+/* ---- SSIM reconstruction term (north_star "masked photometric (L1/SSIM)") --------------------------------------
+ * NOT in the reference (no SSIM anywhere in the checkout): new functionality, PARITY UNPINNED, specified in
+ * csrc/dvf_ssim.cu -- 3x3 average-pool SSIM without padding, C1 = 0.01^2, C2 = 0.03^2, l = clamp((1-SSIM)/2, 0, 1),
+ * loss = sum(m*l) / (B*C*(H-2)*(W-2)) with m = AND of `valid` (nullable, uint8 [B,H,W], dvf_inverse_warp_fwd's mask)
+ * over the window.  x, y [B,C,H,W] fp32; loss: device float; gy (nullable) = d loss / d y, written;
+ * workspace: >= 8 bytes, 8-aligned.                                                                              */
+int dvf_ssim_loss(const float* x, const float* y, const uint8_t* valid, int32_t B, int32_t C, int32_t H, int32_t W,
+                  float* loss, float* gy, void* workspace, void* stream);
+
 /* ---- torch.sin / torch.cos of fp32 values exactly as torch-CPU evaluates them ------------------
  * (reference: inverse_warp.py:89-91,98-99,105-106 -- euler2mat's torch.cos / torch.sin, which on the
  * CPU run MKL's VML in high-accuracy mode).  Bit-identical to torch 2.11 CPU for |x| <= 10000; larger

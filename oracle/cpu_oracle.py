@@ -42,6 +42,7 @@ def lib():
             build()
         _lib = C.CDLL(_SO)
         _lib.dvfo_smooth_loss.restype = C.c_double
+        _lib.dvfo_ssim_loss.restype = C.c_double
         _lib.dvfo_explainability_loss.restype = C.c_double
     return _lib
 
@@ -278,3 +279,13 @@ def caffe_edge_smooth(img, inv_depth, weight=10.0, need_grad=True):
     g = np.empty((N, 1, H, W), np.float32) if need_grad else None
     lib().dvfo_caffe_edge_smooth(_p(img), _p(inv_depth), N, H, W, C.c_float(weight), loss.ctypes.data_as(C.c_void_p), _p(g))
     return loss, g
+
+
+def ssim_loss(x, y, valid=None, need_grad=True):
+    """(loss, gy) of the SSIM term defined in csrc/dvf_ssim.cu (new functionality, PARITY UNPINNED)."""
+    x, y = _f32(x), _f32(y)
+    B, Cc, H, W = x.shape
+    v = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+    g = np.empty_like(y) if need_grad else None
+    loss = lib().dvfo_ssim_loss(_p(x), _p(y), None if v is None else v.ctypes.data_as(C.c_void_p), B, Cc, H, W, _p(g))
+    return float(loss), g

@@ -961,3 +961,50 @@ DVFO_API void dvfo_caffe_edge_smooth(const float *img, const float *invd, int N,
   loss[1] = ly / (double)N;
   free(gx); free(gy); free(ex); free(ey);
 }
+
+/* SSIM reconstruction term -- NOT in the reference (the checkout contains no SSIM): PARITY UNPINNED by construction.  It
+ * restates the definition written in depth-vo-feat_b200/csrc/dvf_ssim.cu (3x3 average-pool SSIM without padding,
+ * C1 = 0.01^2, C2 = 0.03^2, l = clamp((1 - SSIM)/2, 0, 1), mean over B*C*(H-2)*(W-2) windows, windows touching an invalid
+ * pixel contribute zero) in fp64, window by window, and back-propagates each window to its nine pixels (scatter form;
+ * the kernel gathers).  tests/ additionally compare it with a torch restatement (avg_pool2d + autograd). */
+DVFO_API double dvfo_ssim_loss(const float *x, const float *y, const unsigned char *valid, int B, int C, int H, int W,
+                               float *gy) {
+  const double C1 = 0.01 * 0.01, C2 = 0.03 * 0.03, N = (double)B * C * (H - 2) * (W - 2);
+  double total = 0.0;
+  double *g = gy ? (double *)calloc((size_t)B * C * H * W, sizeof(double)) : NULL;
+  for (int p = 0; p < B * C; ++p) {
+    const float *xp = x + (size_t)p * H * W, *yp = y + (size_t)p * H * W;
+    const unsigned char *vp = valid ? valid + (size_t)(p / C) * H * W : NULL;
+    for (int i = 0; i < H - 2; ++i)
+      for (int j = 0; j < W - 2; ++j) {
+        double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+        int m = 1;
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) {
+            const double u = xp[(i + a) * W + j + b], v = yp[(i + a) * W + j + b];
+            sx += u; sy += v; sxx += u * u; syy += v * v; sxy += u * v;
+            if (vp && !vp[(i + a) * W + j + b]) m = 0;
+          }
+        if (!m) continue;
+        const double mx = sx / 9, my = sy / 9, vx = sxx / 9 - mx * mx, vy = syy / 9 - my * my, cxy = sxy / 9 - mx * my;
+        const double A1 = 2 * mx * my + C1, A2 = 2 * cxy + C2, B1 = mx * mx + my * my + C1, B2 = vx + vy + C2;
+        const double S = (A1 * A2) / (B1 * B2), l = 0.5 * (1 - S);
+        total += l < 0 ? 0 : (l > 1 ? 1 : l);
+        if (g && l > 0 && l < 1) {
+          const double d = B1 * B2, k = -0.5 / N;
+          const double dmy = ((2 * mx * A2 - 2 * mx * A1) * d - (A1 * A2) * (2 * my * B2 - 2 * my * B1)) / (d * d);
+          const double dEyy = -(A1 * A2) * B1 / (d * d), dExy = 2 * A1 * B2 * B1 / (d * d);
+          for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+              const size_t q = (size_t)p * H * W + (i + a) * W + j + b;
+              g[q] += k * (dmy + 2.0 * yp[(i + a) * W + j + b] * dEyy + xp[(i + a) * W + j + b] * dExy) / 9.0;
+            }
+        }
+      }
+  }
+  if (g) {
+    for (size_t q = 0; q < (size_t)B * C * H * W; ++q) gy[q] = (float)g[q];
+    free(g);
+  }
+  return total / N;
+}

@@ -62,3 +62,21 @@ class align_corners:
 
 def oracle_pad(name, pad="zeros"):
     return pad + ("_align" if str(name).endswith("_align") else "")
+
+
+def torch_ssim_loss(x, y, valid=None):
+    """The SSIM term of csrc/dvf_ssim.cu written with torch operators (avg_pool2d, autograd): the independent fp32/fp64
+    restatement the kernel and the oracle are compared with (there is no SSIM in the reference)."""
+    import torch
+    import torch.nn.functional as F
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    mx, my = F.avg_pool2d(x, 3, 1), F.avg_pool2d(y, 3, 1)
+    vx = F.avg_pool2d(x * x, 3, 1) - mx * mx
+    vy = F.avg_pool2d(y * y, 3, 1) - my * my
+    cxy = F.avg_pool2d(x * y, 3, 1) - mx * my
+    S = ((2 * mx * my + C1) * (2 * cxy + C2)) / ((mx * mx + my * my + C1) * (vx + vy + C2))
+    l = ((1 - S) / 2).clamp(0, 1)
+    if valid is not None:
+        m = (F.avg_pool2d(valid.to(l.dtype).unsqueeze(1), 3, 1) > 1 - 1e-6).to(l.dtype)
+        l = l * m
+    return l.mean()

@@ -260,3 +260,57 @@ def test_tensors_on_different_devices_are_rejected(ops, syn):
     with pytest.raises(DvfError):
         import inverse_warp as iw
         iw.inverse_warp(d["img_R1"], d["depth"].cuda(), d["T_2to1"].cuda(), d["intrinsics"].cuda(), d["intrinsics_inv"].cuda())
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 19, 37), (1, 1, 3, 3), (3, 3, 128, 416), (2, 8, 33, 65)])
+def test_ssim_loss_vs_oracle_and_torch(ops, shape):
+    """SSIM term (new functionality; parity unpinned, no SSIM in the reference): the CUDA kernel against the C oracle and
+    against the torch restatement on the CPU, fp32, 1e-5."""
+    from helpers import torch_ssim_loss
+    from oracle import cpu_oracle as O
+    O.build()
+    B, Cc, H, W = shape
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(B, Cc, H, W, generator=g)
+    y = (x + 0.3 * torch.rand(B, Cc, H, W, generator=g) - 0.1).clamp(0, 1)
+    valid = (torch.rand(B, H, W, generator=g) > 0.05).to(torch.uint8)
+    for v in (None, valid):
+        yc = y.cuda().requires_grad_(True)
+        loss = ops.ssim_loss(x.cuda(), yc, None if v is None else v.cuda())
+        (2.0 * loss).backward()
+        ol, og = O.ssim_loss(x.numpy(), y.numpy(), None if v is None else v.numpy())
+        yd = y.clone().requires_grad_(True)
+        tl = torch_ssim_loss(x, yd, v)
+        tl.backward()
+        assert abs(loss.item() - ol) <= RTOL_F32 * max(ol, 1e-6), (loss.item(), ol)
+        assert abs(loss.item() - tl.item()) <= 2 * RTOL_F32 * max(tl.item(), 1e-6)
+        if np.abs(og).max() > 0:
+            assert_close(npy(yc.grad), 2.0 * og, tol=RTOL_F32, what="SSIM d/dy vs oracle")
+            assert_close(npy(yc.grad), 2.0 * yd.grad.numpy(), tol=3 * RTOL_F32, what="SSIM d/dy vs torch")
+
+
+def test_ssim_mixed_loss_runs_end_to_end(ops, syn):
+    """loss_functions.photometric_ssim_reconstruction_loss: (1-alpha) L1 + alpha SSIM; gradients equal the sum of the parts."""
+    import inverse_warp as iw
+    import loss_functions as lf
+    d = syn.stereo_temporal_batch(2, 32, 104, seed=5)
+    t = {k: v.cuda() for k, v in d.items()}
+    for k in ("depth", "T_2to1", "T_R2L"):
+        t[k].requires_grad_(True)
+    args = (t["img_R2"], t["img_R1"], t["img_L2"], t["depth"], t["T_2to1"], t["T_R2L"], t["intrinsics"], t["intrinsics_inv"])
+    loss = lf.photometric_ssim_reconstruction_loss(*args, alpha=0.85)
+    loss.backward()
+    got = {k: t[k].grad.clone() for k in ("depth", "T_2to1", "T_R2L")}
+    for k in got:
+        t[k].grad = None
+    l1 = lf.photometric_reconstruction_loss(*args)
+    s = 0
+    for src, pose in (("img_R1", "T_2to1"), ("img_L2", "T_R2L")):
+        w = iw.inverse_warp(t[src], t["depth"], t[pose], t["intrinsics"], t["intrinsics_inv"])
+        s = s + ops.ssim_loss(t["img_R2"], w, (w.detach() != 0).any(1).to(torch.uint8))
+    ref = 0.15 * l1 + 0.85 * s
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
+    assert 0.0 < s.item() < 2.0
+    for k in got:
+        assert_close(npy(got[k]), npy(t[k].grad), tol=1e-6, what=k)

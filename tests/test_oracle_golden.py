@@ -160,3 +160,23 @@ def test_regularisers_match_reference_golden(oracle):
         ref += v
         assert_close(gr, g[f"g_mask{i}"], what=f"expl grad {i}")
     assert abs(ref - float(g["expl"])) <= 1e-5 * float(g["expl"])
+
+
+def test_ssim_oracle_matches_torch_restatement(oracle):
+    """SSIM term (new functionality, parity unpinned -- the reference has none): the C oracle against a torch fp64
+    restatement of the same definition with autograd, with and without a validity mask."""
+    import torch
+    from helpers import torch_ssim_loss
+    g = torch.Generator().manual_seed(3)
+    B, C, H, W = 2, 3, 19, 37
+    x = torch.rand(B, C, H, W, generator=g)
+    y = (x + 0.2 * torch.rand(B, C, H, W, generator=g)).clamp(0, 1)
+    y[0, :, 5:9, 7:12] = x[0, :, 5:9, 7:12]          # identical patches: SSIM = 1, loss 0
+    valid = (torch.rand(B, H, W, generator=g) > 0.1).to(torch.uint8)
+    for v in (None, valid):
+        yd = y.double().requires_grad_(True)
+        ref = torch_ssim_loss(x.double(), yd, v)
+        ref.backward()
+        loss, gy = oracle.ssim_loss(x.numpy(), y.numpy(), None if v is None else v.numpy())
+        assert abs(loss - ref.item()) <= 1e-9 + 1e-7 * abs(ref.item())
+        assert_close(gy, yd.grad.numpy(), tol=1e-6, what="d loss / d y")
