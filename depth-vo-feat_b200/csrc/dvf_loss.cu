@@ -171,6 +171,12 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
   prm.nan_flags = (d->flags & DVF_FLAG_NAN_CHECK) ? d->nan_flags : nullptr;
   if ((d->flags & DVF_FLAG_NAN_CHECK) && !d->nan_flags) return DVF_EINVAL_NULL;
   prm.ctas_per_sm = d->ctas_per_sm;
+  prm.disparity = (d->flags & DVF_FLAG_DISPARITY) ? 1 : 0;
+  prm.disp_eps = d->disp_eps;
+  prm.img_scale = d->img_scale == 0.0f ? 1.0f : d->img_scale;
+  if (prm.img_scale != 1.0f && !(d->C == 3 && d->layout == DVF_NCHW)) return DVF_EUNSUPPORTED;   // images only
+  // the image kernel carries the glue in zeros-padding variants only (the reference's default, and what its callers use)
+  if ((prm.disparity || prm.img_scale != 1.0f) && d->padding != DVF_PAD_ZEROS && uses_c3_kernel(d, levels)) return DVF_EUNSUPPORTED;
   if (d->n_peers < 0 || d->n_peers > DVF_MAX_PEERS || (d->n_peers > 0 && (d->peer_rank < 0 || d->peer_rank >= d->n_peers)))
     return DVF_EINVAL_SHAPE;
   if (d->n_peers > 0 && !d->peer_terms) return DVF_EINVAL_NULL;

@@ -1,4 +1,4 @@
-// explicit instantiations of the fused loss kernels (split over files to build in parallel)
+// explicit instantiations of the fused loss kernels (split over files to build in parallel): zeros padding, 3 and 4 views
 #include "dvf_loss_kernel.cuh"
 
 namespace dvf {
@@ -29,14 +29,7 @@ void launch_loss_c3(const LossParams& prm, int blocks, bool expl, bool grad, boo
   if (tma) launch_loss_c3_t<kV, kZeros, true>(prm, blocks, expl, grad, st);
   else launch_loss_c3_t<kV, kZeros, false>(prm, blocks, expl, grad, st);
 }
-template void launch_loss_c3<1, true>(const LossParams&, int, bool, bool, bool, cudaStream_t);
-template void launch_loss_c3<2, true>(const LossParams&, int, bool, bool, bool, cudaStream_t);
+template void launch_loss_c3<3, true>(const LossParams&, int, bool, bool, bool, cudaStream_t);
+template void launch_loss_c3<4, true>(const LossParams&, int, bool, bool, bool, cudaStream_t);
 }  // namespace dvf
 
-#ifdef DVF_TRACE
-// experiment builds only (not declared in include/dvf_b200.h): per-CTA timestamps of the last zeros-padding image-kernel
-// launch (this translation unit's copy of g_trace)
-DVF_EXPORT int dvf_debug_trace_read(unsigned long long* host_out, int n_ctas) {
-  return (int)cudaMemcpyFromSymbol(host_out, dvf::g_trace, sizeof(unsigned long long) * 8 * n_ctas);
-}
-#endif

@@ -88,6 +88,11 @@ struct LossParams {
   int ctas_per_sm;         // > 0: grid override of the balanced kernels (tuning)
   int grad_bf16;           // NHWC bf16 maps: map gradients are bf16
   int pdl;                 // programmatic dependent launch (DVF_FLAG_PDL)
+  // producer glue folded into the kernel (dvf_loss_desc): `depth` holds disparities, depth = 1 / (disp + disp_eps)
+  // (unsupervise.py:99, train.py:188) and gdepth receives d/d disparity; images are multiplied by img_scale on load
+  // (unsupervise.py:101: 0.004 * img)
+  int disparity;
+  float disp_eps, img_scale;   // img_scale 1 = none
   // balanced split in 32-bit arithmetic (set by launch_balanced once the grid G is known): CTA c owns units
   // [c*q + floor(c*r/G), ...) with T = q*G + r -- the same values as floor(c*T/G) without 64-bit divisions, which cost
   // ~1 us per piece when every issue slot of the SM is contended (profiles/trace_pieces.py)
@@ -217,6 +222,11 @@ __device__ __forceinline__ void pdl_let_successor_start(const LossParams& prm) {
 __device__ __forceinline__ void pdl_wait_predecessor(const LossParams& prm) {
   if (prm.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+
+// depth from the network's disparity exactly as torch evaluates 1 / (disp + eps): a rounded add, then reciprocal()
+// (python's 1 / tensor is tensor.reciprocal() * 1); backward of reciprocal: -g * (depth * depth)
+__device__ __forceinline__ float depth_of_disp(float disp, float eps) { return div(1.0f, add(disp, eps)); }
+__device__ __forceinline__ float gdisp_of_gdepth(float g, float depth) { return mul(-g, mul(depth, depth)); }
 
 // sign(d)/N with sign(0) = sign(NaN) = 0, gated by `gate`
 __device__ __forceinline__ float signed_unit(float d, float inv_n, bool gate) {
@@ -420,7 +430,9 @@ constexpr int c3_min_blocks(int) { return DVF_C3_MINBLOCKS; }
 #else
 constexpr int c3_min_blocks(int views) { return views >= 3 ? 3 : 4; }
 #endif
-template <int kV, bool kZeros, bool kExpl, bool kGrad, bool kTma, int kMinBlocks = c3_min_blocks(kV)>
+// kGlue: the producer glue (disparity -> depth, image scale; dvf_loss_desc) is compiled in.  A separate variant because the
+// three CTA-uniform branches it needs cost the plain path 1.8 % when they are always present (profiles/r2_summary.md).
+template <int kV, bool kZeros, bool kExpl, bool kGrad, bool kTma, bool kGlue = false, int kMinBlocks = c3_min_blocks(kV)>
 __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kernel(const __grid_constant__ LossParams prm) {
   constexpr int kC = 3;
 #ifdef DVF_ACC_SMEM
@@ -465,6 +477,7 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
   DVF_MARK(0);
   int piece_no = 0;
   int prev_b = -1;   // image whose pose / intrinsics sit in shared memory
+  const bool disp_mode = kGlue && prm.disparity != 0, scale_imgs = kGlue && prm.img_scale != 1.0f;   // CTA-uniform
 
   while (w < w_end) {
   const int b = (int)fastdiv((uint32_t)w, prm.div_upi);
@@ -607,6 +620,12 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
         for (int v = 0; v < kV; ++v) exv[v] = make_float2(ld_stream(expl_b + v * HW + ia), ld_stream(expl_b + v * HW + ib));
       }
     }
+    if (disp_mode) dep = make_float2(depth_of_disp(dep.x, prm.disp_eps), depth_of_disp(dep.y, prm.disp_eps));
+    if (scale_imgs) {
+      tg0 = mul2(tg0, dup(prm.img_scale));
+      tg1 = mul2(tg1, dup(prm.img_scale));
+      tg2 = mul2(tg2, dup(prm.img_scale));
+    }
     // dead lanes (past the end of the run) may read stale ring contents: give them a harmless depth; their
     // taps are never loaded (all-zero => invalid => zero gradients) and nothing of theirs is stored
     if (kTail) {
@@ -688,6 +707,15 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
             pa = ptr_off(pa, HW);
             pb = ptr_off(pb, HW);
           }
+        }
+      }
+      if (scale_imgs) {
+#pragma unroll
+        for (int c = 0; c < kC; ++c) {
+          t00[c] = mul2(t00[c], dup(prm.img_scale));
+          t01[c] = mul2(t01[c], dup(prm.img_scale));
+          t10[c] = mul2(t10[c], dup(prm.img_scale));
+          t11[c] = mul2(t11[c], dup(prm.img_scale));
         }
       }
       const f2 ex = kExpl ? exv[kExpl ? v : 0] : dup(1.0f);
@@ -790,6 +818,13 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
       }
     }  // views
     if (kGrad && want_gdepth) {
+      if (disp_mode) {   // d/d disparity; the depth is recomputed from the staged disparity (two registers less to keep alive)
+        const f2 dsp = kTma ? *reinterpret_cast<const f2*>(&s_ring[st][0][slot])
+                            : make_float2(ld_stream(depth_b + (kTail ? min(idxA, HW - 1) : idxA)),
+                                          ld_stream(depth_b + (kTail ? min(idxB, HW - 1) : idxB)));
+        gd = make_float2(gdisp_of_gdepth(gd.x, depth_of_disp(dsp.x, prm.disp_eps)),
+                         gdisp_of_gdepth(gd.y, depth_of_disp(dsp.y, prm.disp_eps)));
+      }
       float* const gp = ptr_off(gdepth_b, idxA);
       if (liveA) st_stream(gp, gd.x);
       if (liveB) st_stream(gp + 1, gd.y);
@@ -877,7 +912,9 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_cn_kernel(const __
 #pragma unroll
       for (int k = 0; k < 9; ++k) M[k] = s_M[k];
       const int i = (int)fastdiv((uint32_t)idx, lv.divW);
-      pixel_to_cam(M, live ? ld_stream(depth_b + idx) : 1.0f, i, idx - i * W, cam);
+      float dv = live ? ld_stream(depth_b + idx) : 1.0f;
+      if (prm.disparity) dv = depth_of_disp(dv, prm.disp_eps);
+      pixel_to_cam(M, dv, i, idx - i * W, cam);
     }
     float gd = 0.0f;
 #pragma unroll
@@ -965,7 +1002,10 @@ __global__ void __launch_bounds__(kLossThreads, 4) photo_loss_cn_kernel(const __
         }
       }
     }
-    if (need_grad && live && lv.gdepth) st_stream(lv.gdepth + (size_t)b * HW + idx, gd);
+    if (need_grad && live && lv.gdepth) {
+      if (prm.disparity) gd = gdisp_of_gdepth(gd, depth_of_disp(ld_stream(depth_b + idx), prm.disp_eps));
+      st_stream(lv.gdepth + (size_t)b * HW + idx, gd);
+    }
   }
   reduce_and_finish<kV, kLossThreads>(acc, prm, lv, l, chunk, lv.blocks_per_image, b, C);
 }

@@ -228,7 +228,9 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
 #pragma unroll
       for (int k = 0; k < 9; ++k) M[k] = s_M[k];
       const int i = (int)fastdiv((uint32_t)idc, lv.divW);
-      pixel_to_cam(M, ld_stream(depth_b + idc), i, idc - i * W, cam);
+      float dv = ld_stream(depth_b + idc);
+      if (prm.disparity) dv = depth_of_disp(dv, prm.disp_eps);
+      pixel_to_cam(M, dv, i, idc - i * W, cam);
     }
 #pragma unroll
     for (int v = 0; v < kV; ++v) {
@@ -410,7 +412,10 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
         const int slot = butterfly_slot(lane);
         if ((lane & 1) == 0 && slot < 12) s_wacc[warp][v][slot] += tot;
       }
-      if (live && lv.gdepth) st_stream(lv.gdepth + img_px + idx, gd);
+      if (live && lv.gdepth) {
+        if (prm.disparity) gd = gdisp_of_gdepth(gd, depth_of_disp(ld_stream(depth_b + idx), prm.disp_eps));
+        st_stream(lv.gdepth + img_px + idx, gd);
+      }
     }
   }
   __syncwarp();

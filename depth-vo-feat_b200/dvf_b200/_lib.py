@@ -17,7 +17,7 @@ F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
 PADDING = {"zeros": 0, "border": 1}
 ROTATION = {"euler": 0, "quat": 1}
-FLAG_ALIGN_CORNERS, FLAG_ZERO_GSRC, FLAG_NAN_CHECK, FLAG_NO_TMA, FLAG_PDL = 1, 2, 4, 8, 16
+FLAG_ALIGN_CORNERS, FLAG_ZERO_GSRC, FLAG_NAN_CHECK, FLAG_NO_TMA, FLAG_PDL, FLAG_DISPARITY = 1, 2, 4, 8, 16, 32
 ABI_VERSION = 2
 
 
@@ -54,7 +54,8 @@ class dvf_loss_desc(C.Structure):
                 ("dtype", C.c_int32), ("layout", C.c_int32), ("padding", C.c_int32), ("flags", C.c_int32),
                 ("mean_batch", C.c_int32), ("grad_dtype", C.c_int32), ("piece_overhead", C.c_int32), ("ctas_per_sm", C.c_int32),
                 ("upstream", C.c_void_p), ("nan_flags", C.c_void_p),
-                ("n_peers", C.c_int32), ("peer_rank", C.c_int32), ("peer_terms", C.POINTER(C.c_void_p))]
+                ("n_peers", C.c_int32), ("peer_rank", C.c_int32), ("peer_terms", C.POINTER(C.c_void_p)),
+                ("disp_eps", C.c_float), ("img_scale", C.c_float)]
 
 
 _vp, _i32, _sz, _fp = C.c_void_p, C.c_int32, C.c_size_t, C.POINTER(C.c_float)

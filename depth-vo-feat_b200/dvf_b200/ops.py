@@ -406,7 +406,7 @@ def area_pyramid(img, sizes: Sequence[Sequence[int]]):
 # ------------------------------------------------------------------------------------------------
 class _LossCfg:
     __slots__ = ("V", "L", "rotation_mode", "padding_mode", "downscales", "has_expl", "expl_channels", "align_corners",
-                 "global_batch", "nan_check")
+                 "global_batch", "nan_check", "disparity_eps", "img_scale")
 
 
 def _scaled(tensors: List[Optional[torch.Tensor]], g: torch.Tensor):
@@ -513,13 +513,15 @@ class _LossCall:
                 if want_grads and self.need_tgt[l]:
                     g_tgt[l] = torch.empty_like(self.tgts[l], dtype=gdt)
                     lv.gtgt = g_tgt[l].data_ptr()
-            flags = _flags(cfg.align_corners) | _lib.FLAG_ZERO_GSRC | (_lib.FLAG_NAN_CHECK if cfg.nan_check else 0)
+            flags = _flags(cfg.align_corners) | _lib.FLAG_ZERO_GSRC | (_lib.FLAG_NAN_CHECK if cfg.nan_check else 0) | \
+                (_lib.FLAG_DISPARITY if cfg.disparity_eps is not None else 0)
             up = None
             if upstream is not None:
                 up = upstream.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
             d = dvf_loss_desc(B, Cc, V, L, self.dtype, self.layout, PADDING[cfg.padding_mode], flags,
                               int(cfg.global_batch or 0), _lib.BF16 if bf16_grads else _lib.F32, 0, 0, _ptr(up),
-                              nan_flags(dev).data_ptr() if cfg.nan_check else None, 0, 0, None)
+                              nan_flags(dev).data_ptr() if cfg.nan_check else None, 0, 0, None,
+                              float(cfg.disparity_eps or 0.0), float(cfg.img_scale))
             nbytes = lib.dvf_photo_loss_workspace_bytes(C.byref(d), levels)
             if nbytes == 0:
                 raise DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")
@@ -583,7 +585,8 @@ class FusedPhotoLoss(torch.autograd.Function):
 
 
 def fused_photo_loss(tgt_levels, src_levels, depth_levels, pose, K, Kinv, expl_levels=None, downscales=None,
-                     rotation_mode="euler", padding_mode="zeros", align_corners=None, global_batch=None, nan_check=False):
+                     rotation_mode="euler", padding_mode="zeros", align_corners=None, global_batch=None, nan_check=False,
+                     disparity_eps=None, img_scale=1.0):
     """tgt_levels: L tensors [B,C,h,w]; src_levels: L lists of V tensors; depth_levels: L tensors [B,h,w];
     pose [B,V,6]; expl_levels: None or L tensors [B,>=V,h,w].  Returns (loss, terms[L*V]).
     global_batch: size of the whole (sharded) batch when this call holds only B of its images (dvf_b200.dist);
@@ -598,6 +601,7 @@ def fused_photo_loss(tgt_levels, src_levels, depth_levels, pose, K, Kinv, expl_l
     cfg.downscales = [1.0] * L if downscales is None else [float(x) for x in downscales]
     cfg.has_expl = expl_levels is not None
     cfg.align_corners, cfg.global_batch, cfg.nan_check = align_corners, global_batch, bool(nan_check)
+    cfg.disparity_eps, cfg.img_scale = disparity_eps, float(img_scale)
     flat = list(tgt_levels) + [s for lvl in src_levels for s in lvl] + list(depth_levels)
     if cfg.has_expl:
         flat += list(expl_levels)

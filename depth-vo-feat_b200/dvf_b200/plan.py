@@ -27,7 +27,8 @@ class FusedLossPlan:
                  map_grads: bool = False, global_batch: Optional[int] = None, align_corners: bool = False,
                  upstream: Optional[torch.Tensor] = None, fused_pose: bool = True, use_tma: bool = True,
                  piece_overhead: int = 0, ctas_per_sm: int = 0, pdl: bool = False,
-                 peer_terms: Optional[Sequence[int]] = None, peer_rank: int = 0, bf16_grads: bool = True):
+                 peer_terms: Optional[Sequence[int]] = None, peer_rank: int = 0, bf16_grads: bool = True,
+                 disparity_eps: Optional[float] = None, img_scale: float = 1.0):
         """Maps: dense NCHW fp32 (images, any C) or channels-last fp32 / bf16 feature maps ([B,C,H,W] tensors in
         torch.channels_last memory).  map_grads: also produce d/d tgt and d/d src (fp32, layout of the maps).
         global_batch: this plan holds B of the global_batch images of a sharded batch (dvf_loss_desc.mean_batch).
@@ -94,7 +95,9 @@ class FusedLossPlan:
                 (0 if use_tma else _lib.FLAG_NO_TMA) | (_lib.FLAG_PDL if pdl else 0)
         self.desc = dvf_loss_desc(B, Cc, V, L, dtype, layout, PADDING[padding_mode], flags, int(global_batch or 0), _lib.BF16 if self.grad_bf16 else _lib.F32,
                                   int(piece_overhead), int(ctas_per_sm), None if upstream is None else upstream.data_ptr(), None,
-                                  0, 0, None)
+                                  0, 0, None, float(disparity_eps or 0.0), float(img_scale))
+        if disparity_eps is not None:
+            self.desc.flags |= _lib.FLAG_DISPARITY   # depth_levels hold disparities; gdepth = d/d disparity
         if peer_terms:
             self._peer_arr = (C.c_void_p * len(peer_terms))(*[int(x) for x in peer_terms])   # keep alive
             self.desc.n_peers, self.desc.peer_rank, self.desc.peer_terms = len(peer_terms), int(peer_rank), self._peer_arr

@@ -22,6 +22,21 @@ def photometric_reconstruction_loss(img_R2, img_R1, img_L2, depth, T_2to1, T_R2L
     return loss
 
 
+def photometric_reconstruction_loss_fused_inputs(img_R2, img_R1, img_L2, inv_depth, T_2to1, T_R2L, intrinsics, intrinsics_inv,
+                                                rotation_mode='euler', padding_mode='zeros', img_scale=0.004, eps=1e-4):
+    """unsupervise.py:99-101 in one launch: the caller's
+        depth = (1/(inv_depth+1e-4)).squeeze(1)
+        photometric_reconstruction_loss(0.004*img_R2, 0.004*img_R1, 0.004*img_L2, depth, ...)
+    with the reciprocal and the three image scalings folded into the fused kernel (they cost more HBM traffic as separate
+    torch passes than the loss itself).  inv_depth [B,1,H,W] or [B,H,W]: the DispNet output; gradients flow to it."""
+    disp = inv_depth.squeeze(1) if inv_depth.dim() == 4 else inv_depth
+    pose = torch.stack((T_2to1, T_R2L), dim=1)
+    loss, _ = _ops.fused_photo_loss([img_R2], [[img_R1, img_L2]], [disp], pose, intrinsics, intrinsics_inv,
+                                    rotation_mode=rotation_mode, padding_mode=padding_mode, disparity_eps=eps,
+                                    img_scale=img_scale)
+    return loss
+
+
 def smooth_loss(pred_map, scale_factor=1):
     """loss_functions.py:23-41: second-order smoothness, sum over scales with weight /= scale_factor.
     One fused CUDA launch for all scales (value + gradient, csrc/dvf_reg.cu)."""

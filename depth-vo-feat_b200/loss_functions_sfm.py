@@ -34,8 +34,10 @@ def _as_list(x):
 
 
 def photometric_reconstruction_loss(tgt_img, ref_imgs, intrinsics, intrinsics_inv, depth, explainability_mask, pose,
-                                    rotation_mode='euler', padding_mode='zeros'):
-    """loss_functions_sfm.py:9-46."""
+                                    rotation_mode='euler', padding_mode='zeros', disparity_eps=None):
+    """loss_functions_sfm.py:9-46.  disparity_eps (extension): when not None, `depth` holds the DispNet disparities and
+    the kernel evaluates depth = 1 / (disp + disparity_eps) itself -- train.py:188's `depth = [1/disp for disp in
+    disparities]` (eps 0) folded into the launch; gradients then flow to the disparities."""
     masks = _as_list(explainability_mask)
     depths = _as_list(depth)
     n = min(len(depths), len(masks))           # zip() semantics of :44
@@ -53,7 +55,8 @@ def photometric_reconstruction_loss(tgt_img, ref_imgs, intrinsics, intrinsics_in
     src_levels = [[ref_pyr[v][l] for v in range(len(ref_imgs))] for l in range(n)]
     loss, _ = _ops.fused_photo_loss(tgt_pyr, src_levels, [d[:, 0] for d in depths], pose, intrinsics, intrinsics_inv,
                                     expl_levels=masks if has_mask else None, downscales=downscales,
-                                    rotation_mode=rotation_mode, padding_mode=padding_mode, nan_check=NAN_CHECK)
+                                    rotation_mode=rotation_mode, padding_mode=padding_mode, nan_check=NAN_CHECK,
+                                    disparity_eps=disparity_eps)
     return loss
 
 

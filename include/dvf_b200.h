@@ -78,7 +78,12 @@ typedef enum dvf_flags {
    * pose backward) still run.  The kernel does not wait for the PREVIOUS kernel of the stream until just before it
    * exits.  CONTRACT: the previous kernel in the stream shares NO buffer with this launch -- it writes none of its
    * inputs and touches none of its outputs, and the two launches use different workspaces.                    */
-  DVF_FLAG_PDL = 16
+  DVF_FLAG_PDL = 16,
+  /* loss entries: producer glue folded into the kernel.  dvf_level.depth holds the network's
+   * DISPARITY; the kernel uses depth = 1 / (disp + dvf_loss_desc.disp_eps) -- `1/(inv_depth+1e-4)` of
+   * unsupervise.py:99, `1/disp` of train.py:188 (eps 0) -- evaluated as torch does (rounded add, reciprocal), and
+   * dvf_level.gdepth receives d/d disparity = -g_depth * depth^2.                                              */
+  DVF_FLAG_DISPARITY = 32
 } dvf_flags;
 
 /* Image-tensor descriptor shared by the warp and loss entries. */
@@ -197,6 +202,9 @@ typedef struct dvf_loss_desc {
    * order).  n_peers = 0: no exchange.                                                                         */
   int32_t n_peers, peer_rank;
   float* const* peer_terms;
+  float disp_eps;         /* DVF_FLAG_DISPARITY: depth = 1 / (disp + disp_eps)                                  */
+  float img_scale;        /* images (C = 3, NCHW) are multiplied by this on load: tgt and src hold the RAW images and
+                             the loss is that of img_scale * img (unsupervise.py:101 passes 0.004 * img); 0 or 1 = none */
 } dvf_loss_desc;
 #define DVF_MAX_PEERS 8
 

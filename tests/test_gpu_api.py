@@ -314,3 +314,45 @@ def test_ssim_mixed_loss_runs_end_to_end(ops, syn):
     assert 0.0 < s.item() < 2.0
     for k in got:
         assert_close(npy(got[k]), npy(t[k].grad), tol=1e-6, what=k)
+
+
+def test_producer_glue_matches_separate_torch_passes(ops, syn):
+    """DVF_FLAG_DISPARITY / img_scale: the reciprocal of unsupervise.py:99 and the 0.004 * img scalings of
+    :101 folded into the launch give the loss and gradients of the separate torch passes (which are exact fp32 element-wise
+    ops): loss and d/d disparity at 1e-5, validity-sensitive terms identical."""
+    import loss_functions as lf
+    import loss_functions_sfm as sfm
+    B, H, W = 3, 32, 104
+    d = syn.stereo_temporal_batch(B, H, W, seed=31)
+    t = {k: v.cuda() for k, v in d.items()}
+    raw = {k: (t[k] / 0.004).contiguous() for k in ("img_R2", "img_R1", "img_L2")}     # uint8-range images
+    inv = (1.0 / t["depth"] - 1e-4).unsqueeze(1).contiguous()
+    a = inv.clone().requires_grad_(True)
+    pa, pb = t["T_2to1"].clone().requires_grad_(True), t["T_R2L"].clone().requires_grad_(True)
+    depth = (1 / (a + 1e-4)).squeeze(1)
+    ref = lf.photometric_reconstruction_loss(0.004 * raw["img_R2"], 0.004 * raw["img_R1"], 0.004 * raw["img_L2"], depth, pa, pb,
+                                             t["intrinsics"], t["intrinsics_inv"])
+    ref.backward()
+    b = inv.clone().requires_grad_(True)
+    qa, qb = t["T_2to1"].clone().requires_grad_(True), t["T_R2L"].clone().requires_grad_(True)
+    got = lf.photometric_reconstruction_loss_fused_inputs(raw["img_R2"], raw["img_R1"], raw["img_L2"], b, qa, qb,
+                                                          t["intrinsics"], t["intrinsics_inv"])
+    got.backward()
+    assert abs(got.item() - ref.item()) <= 1e-6 * abs(ref.item())
+    assert_close(npy(b.grad), npy(a.grad), tol=RTOL_F32, what="d inv_depth")
+    assert_close(npy(qa.grad), npy(pa.grad), tol=RTOL_F32, what="d T_2to1")
+    assert_close(npy(qb.grad), npy(pb.grad), tol=RTOL_F32, what="d T_R2L")
+    # multi-scale form (train.py:188, eps 0)
+    disps = [(1.0 / syn.depth(B, H >> s, W >> s, 40 + s)).cuda().unsqueeze(1) for s in range(2)]
+    pose = torch.stack([t["T_2to1"], t["T_R2L"]], 1)
+    x = [v.clone().requires_grad_(True) for v in disps]
+    r2 = sfm.photometric_reconstruction_loss(t["img_R2"], [t["img_R1"], t["img_L2"]], t["intrinsics"], t["intrinsics_inv"],
+                                             [1 / v for v in x], [None, None], pose)
+    r2.backward()
+    y = [v.clone().requires_grad_(True) for v in disps]
+    g2 = sfm.photometric_reconstruction_loss(t["img_R2"], [t["img_R1"], t["img_L2"]], t["intrinsics"], t["intrinsics_inv"], y,
+                                             [None, None], pose, disparity_eps=0.0)
+    g2.backward()
+    assert abs(g2.item() - r2.item()) <= 1e-6 * abs(r2.item())
+    for u, v in zip(x, y):
+        assert_close(npy(v.grad), npy(u.grad), tol=RTOL_F32, what="d disparity (multi-scale)")
