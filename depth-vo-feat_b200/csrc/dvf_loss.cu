@@ -61,7 +61,9 @@ static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) 
     // fixed cost of a piece in units.  Image kernel, measured on C2 (V = 1): 2 -> 73.7 us, 3 -> 69.6, 4 -> 67.4,
     // 5 -> 67.4, 6 -> 68.5, 8 -> 69.7; with V = 2 a unit is twice the work: 3 -> 120.1 us, 4 -> 122.6, 6 -> 125.4.
     // A unit of the channels-last kernel is C/kVec times more work again, so its pieces cost less than one unit.
-    const int by_views = d->V == 1 ? 4 : (d->V == 2 ? 3 : 2);
+    // round 2 (programmatic dependent launch, cheaper pieces), C2: 3 -> 53.8 us, 4 -> 52.2, 5 -> 51.4, 6 -> 51.4, 8 -> 51.6,
+    // 10 -> 52.0; V = 2 (C3 / C5loss shapes) is flat between 2 and 6.
+    const int by_views = d->V == 1 ? 5 : (d->V == 2 ? 3 : 2);
     pl.piece_overhead = d->piece_overhead > 0 ? d->piece_overhead : (d->layout == DVF_NHWC ? 0 : by_views);
   }
   long long per_image = 0;
