@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_fwd_kernel(const __grid
   }
 }
 
-template <bool kZeros>
+// kCT: compile-time channel count (3 = images: the channel loops unroll and their loads overlap), 0 = run time
+template <bool kZeros, int kCT>
 __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_kernel(const __grid_constant__ WarpParams p) {
   __shared__ float s_red[kThreads / 32][kRedSlots];
   __shared__ int s_flag;
@@ -103,17 +104,19 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_kernel(const __grid
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float P[12], M[9];
   load_PM(p, b, P, M);
-  const int HW = p.HW, W = p.W, H = p.H;
-  const float* img_b = p.img + (size_t)b * p.C * HW;
-  const float* gout_b = p.gout + (size_t)b * p.C * HW;
-  float* gimg_b = p.gimg ? p.gimg + (size_t)b * p.C * HW : nullptr;
+  const int HW = p.HW, W = p.W, H = p.H, C = kCT ? kCT : p.C;
+  const float* img_b = p.img + (size_t)b * C * HW;
+  const float* gout_b = p.gout + (size_t)b * C * HW;
+  float* gimg_b = p.gimg ? p.gimg + (size_t)b * C * HW : nullptr;
   float acc[kRedSlots];
 #pragma unroll
   for (int k = 0; k < kRedSlots; ++k) acc[k] = 0.0f;
 
   for (int it = 0; it < p.bwd_iters * kWarpPPT; ++it) {
-    const int idx = chunk0 * (kThreads * kWarpPPT) + it * kThreads + tid;
-    if (idx >= HW) break;
+    const int idx_raw = chunk0 * (kThreads * kWarpPPT) + it * kThreads + tid;
+    const bool live = idx_raw < HW;
+    if (__all_sync(0xffffffffu, !live)) break;   // warp-uniform: the lanes of a warp stay together for the shuffles below
+    const int idx = live ? idx_raw : HW - 1;
     const int i = (int)fastdiv((uint32_t)idx, p.divW), j = idx - i * W;
     Cam cam;
     Proj pr;
@@ -124,30 +127,56 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_kernel(const __grid
     locate<kZeros>(pr.xn, pr.yn, H, W, p.geo, L);
     const int o_nw = L.y0 * W + L.x0;
     const float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
+    // Scatter of d img, warp-aggregated: neighbouring lanes are neighbouring target pixels, and where the sampling
+    // positions advance by one texel (the usual case: smooth depth) the east taps of a lane are the west taps of the next
+    // one.  Such a lane hands its two east contributions to its neighbour (one shuffle each) instead of issuing atomics for
+    // them: 4 -> ~2 atomics per pixel and channel.
+    bool give = false, take = false;
+    if (gimg_b) {
+      // same row, next column (comparing linear offsets would alias (W-1, r) + 1 with (-1, r+1))
+      const int x_next = __shfl_down_sync(0xffffffffu, L.x0, 1), y_next = __shfl_down_sync(0xffffffffu, L.y0, 1);
+      const bool live_next = __shfl_down_sync(0xffffffffu, (int)live, 1) != 0;
+      give = lane < 31 && live && live_next && y_next == L.y0 && x_next == L.x0 + 1;
+      take = __shfl_up_sync(0xffffffffu, (int)give, 1) != 0 && lane > 0;
+    }
     float gx = 0.0f, gy = 0.0f;
-    for (int c = 0; c < p.C; ++c) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
       const float* pl = img_b + (size_t)c * HW + o_nw;
-      const float g = ld_stream(gout_b + (size_t)c * HW + idx);
+      const float g = live ? ld_stream(gout_b + (size_t)c * HW + idx) : 0.0f;
       const float a0 = L.bnw ? __ldg(pl) : 0.0f, a1 = L.bne ? __ldg(pl + 1) : 0.0f;
       const float a2 = L.bsw ? __ldg(pl + W) : 0.0f, a3 = L.bse ? __ldg(pl + W + 1) : 0.0f;
       bilerp_grad(a0, a1, a2, a3, L, g, gx, gy);
       if (gimg_b) {
         float* gp = gimg_b + (size_t)c * HW + o_nw;
-        if (L.bnw) atomicAdd(gp, mul(wnw, g));
-        if (L.bne) atomicAdd(gp + 1, mul(wne, g));
-        if (L.bsw) atomicAdd(gp + W, mul(wsw, g));
-        if (L.bse) atomicAdd(gp + W + 1, mul(wse, g));
+        float c_nw = L.bnw ? mul(wnw, g) : 0.0f, c_sw = L.bsw ? mul(wsw, g) : 0.0f;
+        const float c_ne = L.bne ? mul(wne, g) : 0.0f, c_se = L.bse ? mul(wse, g) : 0.0f;
+        const float r_ne = __shfl_up_sync(0xffffffffu, c_ne, 1), r_se = __shfl_up_sync(0xffffffffu, c_se, 1);
+        if (take) {   // same texels as my west taps (in bounds for both or for neither)
+          c_nw += r_ne;
+          c_sw += r_se;
+        }
+        if (live) {
+          if (L.bnw) atomicAdd(gp, c_nw);
+          if (L.bsw) atomicAdd(gp + W, c_sw);
+          if (!give) {
+            if (L.bne) atomicAdd(gp + 1, c_ne);
+            if (L.bse) atomicAdd(gp + W + 1, c_se);
+          }
+        }
       }
     }
     ChainGrad cg;
     chain_backward<false>(P, cam, pr, L, gx, gy, p.geo, cg);
     if (__builtin_expect(!fast, 0)) cg = warp_chain_backward_exact(p.P + b * 12, cam, pr, L, gx, gy, p.geo);
-    st_stream(p.gdepth + (size_t)b * HW + idx, cg.gdepth);
+    if (live) {
+      st_stream(p.gdepth + (size_t)b * HW + idx, cg.gdepth);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
+      for (int r = 0; r < 3; ++r) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) acc[r * 4 + k] = fmaf(cg.gq[r], cam.cam[k], acc[r * 4 + k]);
-      acc[r * 4 + 3] += cg.gq[r];
+        for (int k = 0; k < 3; ++k) acc[r * 4 + k] = fmaf(cg.gq[r], cam.cam[k], acc[r * 4 + k]);
+        acc[r * 4 + 3] += cg.gq[r];
+      }
     }
   }
 
@@ -279,7 +308,12 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_fwd_c3x2_kernel(const _
   if (p.valid) *reinterpret_cast<uchar2*>(p.valid + (size_t)b * HW + idxA) = make_uchar2(anyA ? 1 : 0, anyB ? 1 : 0);
 }
 
-template <bool kZeros>
+// kScatter: also accumulate d img (p.gimg, zero-filled by the caller).  A thread's two pixels are horizontal neighbours and
+// so are the pairs of neighbouring lanes: where the sampling positions advance by one texel per pixel (smooth depth, the
+// usual case) the east taps of a pixel are the west taps of the next one, so their contributions are added in registers
+// (inside the pair) or handed over by one shuffle (between lanes) before anything goes to memory: ~1 atomic per pixel, row
+// and channel instead of 2 -- and nothing at all changes for the arithmetic of d depth / d P.
+template <bool kZeros, bool kScatter>
 __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_c3x2_kernel(const __grid_constant__ WarpParams p) {
   __shared__ float s_red[kThreads / 32][kRedSlots];
   __shared__ int s_flag;
@@ -295,22 +329,70 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_c3x2_kernel(const _
   const Geo2 geo2 = make_geo2(p.geo);
   const float depth_max = pair_depth_max(p, P, M);
   const float* img_b = p.img + (size_t)b * 3 * HW;
+  float* const gimg_b = kScatter ? p.gimg + (size_t)b * 3 * HW : nullptr;
 #pragma unroll 1
   for (int it = 0; it < p.bwd_iters; ++it) {
-    const int idxA = (chunk0 + it) * (kThreads * 2) + 2 * tid;
-    if (idxA >= HW) break;
+    const int idx_raw = (chunk0 + it) * (kThreads * 2) + 2 * tid;
+    const bool live = idx_raw < HW;               // HW is even: a pair is live or dead as a whole
+    if (kScatter ? __all_sync(0xffffffffu, !live) : !live) break;   // kScatter: lanes stay together for the shuffles
+    const int idxA = live ? idx_raw : HW - 2;
     const float* gout_b = p.gout + (size_t)b * 3 * HW + idxA;
     PairCtx x;
     pair_forward<kZeros>(p, P, M, geo2, depth_max, b, idxA, ld_stream2(p.depth + (size_t)b * HW + idxA), x);
     const Loc2& L = x.L;
-    const float* pa = ptr_off(img_b, L.y0A * W + L.x0A);
-    const float* pb = ptr_off(img_b, L.y0B * W + L.x0B);
+    const int oA = L.y0A * W + L.x0A, oB = L.y0B * W + L.x0B;
+    const float* pa = ptr_off(img_b, oA);
+    const float* pb = ptr_off(img_b, oB);
+    bool adjAB = false, give = false, take = false;
+    f2 wnw, wne, wsw, wse;
+    if (kScatter) {
+      // same row, next column (comparing linear offsets would alias (W-1, r) + 1 with (-1, r+1))
+      adjAB = L.y0B == L.y0A && L.x0B == L.x0A + 1;             // B's west taps are A's east taps
+      const int xA_next = __shfl_down_sync(0xffffffffu, L.x0A, 1), yA_next = __shfl_down_sync(0xffffffffu, L.y0A, 1);
+      const bool live_next = __shfl_down_sync(0xffffffffu, (int)live, 1) != 0;
+      give = lane < 31 && live && live_next && yA_next == L.y0B && xA_next == L.x0B + 1;   // my B's east = the next lane's A's west
+      take = __shfl_up_sync(0xffffffffu, (int)give, 1) != 0 && lane > 0;
+      wnw = mul2(L.s, L.e); wne = mul2(L.s, L.w); wsw = mul2(L.n, L.e); wse = mul2(L.n, L.w);
+    }
     f2 gx = dup(0.0f), gy = dup(0.0f);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       f2 t00, t01, t10, t11;
       pair_taps(L, pa, pb, W, t00, t01, t10, t11);
-      bilerp_grad2(t00, t01, t10, t11, L, ld_stream2(gout_b + (size_t)c * HW), gx, gy);
+      const f2 g = ld_stream2(gout_b + (size_t)c * HW);
+      bilerp_grad2(t00, t01, t10, t11, L, g, gx, gy);
+      if (kScatter) {
+        // contributions of the 8 taps (zero where the texel is outside the image)
+        const f2 cnw = mul2(wnw, g), cne = mul2(wne, g), csw = mul2(wsw, g), cse = mul2(wse, g);
+        float a_nw = L.nwA ? cnw.x : 0.0f, a_sw = L.swA ? csw.x : 0.0f;
+        const float a_ne = L.neA ? cne.x : 0.0f, a_se = L.seA ? cse.x : 0.0f;
+        const float b_nw = L.nwB ? cnw.y : 0.0f, b_sw = L.swB ? csw.y : 0.0f;
+        const float b_ne = L.neB ? cne.y : 0.0f, b_se = L.seB ? cse.y : 0.0f;
+        const float r_ne = __shfl_up_sync(0xffffffffu, b_ne, 1), r_se = __shfl_up_sync(0xffffffffu, b_se, 1);
+        if (take) {
+          a_nw += r_ne;
+          a_sw += r_se;
+        }
+        if (live) {
+          float* ga = ptr_off(gimg_b + (size_t)c * HW, oA);
+          float* gb = ptr_off(gimg_b + (size_t)c * HW, oB);
+          if (L.nwA) atomicAdd(ga, a_nw);
+          if (L.swA) atomicAdd(ga + W, a_sw);
+          if (adjAB) {   // texel oA+1 == oB: one atomic for A's east and B's west tap (both in bounds or neither)
+            if (L.nwB) atomicAdd(gb, a_ne + b_nw);
+            if (L.swB) atomicAdd(gb + W, a_se + b_sw);
+          } else {
+            if (L.neA) atomicAdd(ga + 1, a_ne);
+            if (L.seA) atomicAdd(ga + W + 1, a_se);
+            if (L.nwB) atomicAdd(gb, b_nw);
+            if (L.swB) atomicAdd(gb + W, b_sw);
+          }
+          if (!give) {
+            if (L.neB) atomicAdd(gb + 1, b_ne);
+            if (L.seB) atomicAdd(gb + W + 1, b_se);
+          }
+        }
+      }
       pa = ptr_off(pa, HW);
       pb = ptr_off(pb, HW);
     }
@@ -351,6 +433,7 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_bwd_c3x2_kernel(const _
         }
       }
     }
+    if (!live) continue;
     st_stream2(p.gdepth + (size_t)b * HW + idxA, cg.gdepth);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -604,13 +687,21 @@ DVF_EXPORT int dvf_inverse_warp_bwd(const dvf_desc* d, const void* gout, const v
                                               align_up((size_t)p.blocks_per_image * p.B * kRedSlots * sizeof(float), 256));
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)(p.bwd_blocks_per_image * p.B);
-  const bool packed = p.C == 3 && !p.gimg && p.HW % 2 == 0 && aligned(depth, 8) && aligned(gdepth, 8) && aligned(gout, 8);
-  if (packed) {
-    if (p.zeros_padding) inverse_warp_bwd_c3x2_kernel<true><<<grid, kThreads, 0, cs>>>(p);
-    else inverse_warp_bwd_c3x2_kernel<false><<<grid, kThreads, 0, cs>>>(p);
+  const bool packed = p.C == 3 && p.HW % 2 == 0 && aligned(depth, 8) && aligned(gdepth, 8) && aligned(gout, 8);
+  if (packed && p.gimg) {
+    if (p.zeros_padding) inverse_warp_bwd_c3x2_kernel<true, true><<<grid, kThreads, 0, cs>>>(p);
+    else inverse_warp_bwd_c3x2_kernel<false, true><<<grid, kThreads, 0, cs>>>(p);
+  } else if (packed) {
+    if (p.zeros_padding) inverse_warp_bwd_c3x2_kernel<true, false><<<grid, kThreads, 0, cs>>>(p);
+    else inverse_warp_bwd_c3x2_kernel<false, false><<<grid, kThreads, 0, cs>>>(p);
   } else {
-    if (p.zeros_padding) inverse_warp_bwd_kernel<true><<<grid, kThreads, 0, cs>>>(p);
-    else inverse_warp_bwd_kernel<false><<<grid, kThreads, 0, cs>>>(p);
+    if (p.C == 3) {
+      if (p.zeros_padding) inverse_warp_bwd_kernel<true, 3><<<grid, kThreads, 0, cs>>>(p);
+      else inverse_warp_bwd_kernel<false, 3><<<grid, kThreads, 0, cs>>>(p);
+    } else {
+      if (p.zeros_padding) inverse_warp_bwd_kernel<true, 0><<<grid, kThreads, 0, cs>>>(p);
+      else inverse_warp_bwd_kernel<false, 0><<<grid, kThreads, 0, cs>>>(p);
+    }
   }
   return launch_status();
 }

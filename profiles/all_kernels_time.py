@@ -15,7 +15,7 @@ if not peak:
         peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         peak = 6545.0
-dev = torch.device("cuda"); B, C, H, W = a.batch, 3, bench.H, bench.W; HW = H * W
+dev = torch.device("cuda"); B, C, H, W = a.batch, 3, 128, 416; HW = H * W
 SETS = 6
 
 

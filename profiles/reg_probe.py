@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, torch
 from dvf_b200 import ops, synthetic as syn, _lib
 from dvf_b200._lib import dvf_reg_level
-lib = _lib.load(); dev = torch.device("cuda"); B, H, W = 64, bench.H, bench.W
+lib = _lib.load(); dev = torch.device("cuda"); B, H, W = 64, 128, 416
 def run(kind, maps):
     L = len(maps); levels = (dvf_reg_level * L)(); gs = [torch.empty_like(m) for m in maps]
     for l, (m, g) in enumerate(zip(maps, gs)):
