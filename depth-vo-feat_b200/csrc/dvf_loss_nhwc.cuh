@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
       const float ex = (has_expl && live) ? ld_stream(lv.expl + (size_t)b * lv.expl_bstride + (size_t)v * HW + idc) : 1.0f;
       float4* cell = reinterpret_cast<float4*>(&s_cell[warp][v][lane][0]);
       cell[0] = make_float4(__int_as_float(L.y0 * W + L.x0), __uint_as_float(pk), L.w, L.e);
-      cell[1] = make_float4(L.n, L.s, ex, 0.0f);
+      cell[1] = make_float4(L.n, L.s, ex, __int_as_float(L.x0));
     }
     __syncwarp();
 
@@ -350,16 +350,39 @@ __global__ void __launch_bounds__(kLossThreads, DVF_NHWC_MINBLOCKS) photo_loss_n
             bilerp_grad(a0[c], a1[c], a2[c], a3[c], L, -g[c], gx, gy);
           }
           group_sum_dispatch(lpp_shift, gx, gy, ge, has_expl);   // sums over all channels of the pixel
-          if (gsrc_b[v] && any) {               // scatter: one 16-byte reduction per tap per quad of channels
+          if (gsrc_b[v]) {   // warp-uniform
+            // Scatter: one 16-byte reduction per tap and quad of channels.  Neighbouring lane groups hold neighbouring
+            // target pixels; where the sampling position advances by exactly one texel (same row, next column -- the usual
+            // case) the east taps of a group are the west taps of the next one: it hands its two east contributions over
+            // (shuffles) and the neighbour folds them into its own west reductions -- 4 -> ~2 reductions per pixel and view.
+            const int o_cell = __float_as_int(cw[v].x), x0_cell = __float_as_int(c1.w);
+            const int o_nx = __shfl_down_sync(kFull, o_cell, lpp), x_nx = __shfl_down_sync(kFull, x0_cell, lpp);
+            const bool any_nx = __shfl_down_sync(kFull, (int)any, lpp) != 0;
+            const bool give = (lane + lpp < 32) && any && any_nx && o_nx == o_cell + 1 && x_nx == x0_cell + 1;
+            const bool take = (__shfl_up_sync(kFull, (int)give, lpp) != 0) && lane >= lpp;
             const int o_e = kBf16 ? o_b[v] * 2 : o_b[v];   // byte offset in the fp32 gradient map
             char* const gs = static_cast<char*>(static_cast<void*>(gsrc_b[v]));
 #pragma unroll
             for (int q = 0; q < kVec; q += 4) {
+              float cnw[4], cne[4], csw[4], cse[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                cnw[k] = -g[q + k] * wnw; cne[k] = -g[q + k] * wne; csw[k] = -g[q + k] * wsw; cse[k] = -g[q + k] * wse;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float r_ne = __shfl_up_sync(kFull, cne[k], lpp), r_se = __shfl_up_sync(kFull, cse[k], lpp);
+                if (take) {
+                  cnw[k] += r_ne;
+                  csw[k] += r_se;
+                }
+              }
               const int oq = o_e + (q / 4) * (C / 2) * 4;   // second group of 4 channels: C/2 further
-              red_add_v4(gs, oq, pk & 1u, -g[q] * wnw, -g[q + 1] * wnw, -g[q + 2] * wnw, -g[q + 3] * wnw);
-              red_add_v4(gs, oq + C * 4, pk & 2u, -g[q] * wne, -g[q + 1] * wne, -g[q + 2] * wne, -g[q + 3] * wne);
-              red_add_v4(gs, oq + W * C * 4, pk & 4u, -g[q] * wsw, -g[q + 1] * wsw, -g[q + 2] * wsw, -g[q + 3] * wsw);
-              red_add_v4(gs, oq + W * C * 4 + C * 4, pk & 8u, -g[q] * wse, -g[q + 1] * wse, -g[q + 2] * wse, -g[q + 3] * wse);
+              const unsigned on = any ? 1u : 0u, east = (any && !give) ? 1u : 0u;
+              red_add_v4(gs, oq, (pk & 1u) * on, cnw[0], cnw[1], cnw[2], cnw[3]);
+              red_add_v4(gs, oq + C * 4, (pk & 2u) * east, cne[0], cne[1], cne[2], cne[3]);
+              red_add_v4(gs, oq + W * C * 4, (pk & 4u) * on, csw[0], csw[1], csw[2], csw[3]);
+              red_add_v4(gs, oq + W * C * 4 + C * 4, (pk & 8u) * east, cse[0], cse[1], cse[2], cse[3]);
             }
           }
           // hand the folded sums to the owner lane of the pixel
