@@ -97,6 +97,38 @@ __global__ void __launch_bounds__(256) transpose_tiles_kernel(const T* __restric
 using namespace dvf;
 
 // src [B, R, S] -> dst [B, S, R]; elem_bytes 4 (fp32) or 2 (bf16 / fp16)
+// fp32 transpose that also multiplies by a device scalar: the gradient maps of the channels-last feature loss go back to
+// the reference's dense NCHW layout and take the upstream gradient in the same pass
+__global__ void __launch_bounds__(256) transpose_scale_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int S,
+                                                              const float* __restrict__ scale) {
+  __shared__ float tile[32][33];
+  const float sc = scale ? __ldg(scale) : 1.0f;
+  const size_t img = (size_t)blockIdx.z * R * S;
+  const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int r = r0 + ty + k, sidx = s0 + tx;
+    if (r < R && sidx < S) tile[ty + k][tx] = src[img + (size_t)r * S + sidx];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int sidx = s0 + ty + k, r = r0 + tx;
+    if (r < R && sidx < S) dst[img + (size_t)sidx * R + r] = __fmul_rn(tile[tx][ty + k], sc);
+  }
+}
+
+DVF_EXPORT int dvf_transpose_planes_scaled(const float* src, float* dst, int32_t B, int32_t R, int32_t S, const float* scale,
+                                           void* stream) {
+  if (!src || !dst) return DVF_EINVAL_NULL;
+  if (B <= 0 || R <= 0 || S <= 0 || B > 65535) return DVF_EINVAL_SHAPE;
+  const dim3 grid((S + 31) / 32, (R + 31) / 32, B);
+  if (grid.y > 65535) return DVF_EINVAL_SHAPE;
+  transpose_scale_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, R, S, scale);
+  return launch_status();
+}
+
 DVF_EXPORT int dvf_transpose_planes(const void* src, void* dst, int32_t B, int32_t R, int32_t S, int32_t elem_bytes, void* stream) {
   if (!src || !dst) return DVF_EINVAL_NULL;
   if (B <= 0 || R <= 0 || S <= 0 || B > 65535 || (R + 31) / 32 > 65535) return DVF_EINVAL_SHAPE;

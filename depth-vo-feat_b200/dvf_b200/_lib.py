@@ -80,6 +80,7 @@ SIGNATURES = {
     "dvf_area_pyramid": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "dvf_area_downsample": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "dvf_transpose_planes": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "dvf_transpose_planes_scaled": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "dvf_reg_workspace_bytes": (_sz, [C.POINTER(dvf_reg_level), _i32]),
     "dvf_smooth_loss": (C.c_int, [C.POINTER(dvf_reg_level), _i32, _vp, _vp, _sz, _vp]),
     "dvf_explainability_loss": (C.c_int, [C.POINTER(dvf_reg_level), _i32, _vp, _vp, _sz, _vp]),

@@ -443,6 +443,8 @@ class _LossCall:
         self.pose = _req(pose, "pose", 3)
         self.K, self.Kinv = _req(K, "intrinsics", 3), _req(Kinv, "intrinsics_inv", 3)
         maps, self.layout, self.dtype = _req_maps(list(tensors[0:L + L * V]), "tgt/src")
+        # dense NCHW feature maps that were re-laid out channels-last on the way in (the reference's FeatExtractor output)
+        self.relaid = [m is not t and self.layout == _lib.NHWC and t.is_contiguous() for m, t in zip(maps, tensors[0:L + L * V])]
         self.tgts, self.srcs = maps[0:L], maps[L:L + L * V]
         self.in_dtypes = [t.dtype for t in tensors[0:L + L * V]]
         self.depths = [_req(t, "depth", 3) for t in tensors[L + L * V:2 * L + L * V]]
@@ -543,6 +545,19 @@ class _LossCall:
             return terms, [g_pose] + g_tgt + g_src + g_depth + (g_expl if cfg.has_expl else [])
 
 
+def _nhwc_to_nchw_scaled(g: Optional[torch.Tensor], scale: torch.Tensor):
+    """channels-last fp32 gradient map -> dense NCHW, multiplied by the device scalar `scale` in the same pass"""
+    if g is None:
+        return None
+    B, Cc, H, W = g.shape
+    out = torch.empty(B, Cc, H, W, device=g.device, dtype=torch.float32)
+    sc = scale.detach().to(device=g.device, dtype=torch.float32).reshape(1).contiguous()
+    with _same_device(g):
+        _lib.check(_lib.load().dvf_transpose_planes_scaled(g.data_ptr(), out.data_ptr(), B, H * W, Cc, sc.data_ptr(), _stream()),
+                   "dvf_transpose_planes_scaled")
+    return out
+
+
 class FusedPhotoLoss(torch.autograd.Function):
     """sum over levels and views of mean|(tgt - warp(src_v)) * valid_v [* expl_v]| (dvf_photo_loss_fused_pose).
 
@@ -552,7 +567,10 @@ class FusedPhotoLoss(torch.autograd.Function):
         called again (retain_graph=True);
       * gradients to the maps (feature losses): forward() runs the kernel forward-only, backward() runs the fused pass
         with the upstream scalar handed over as a device pointer -- scaling three full feature-map gradients after
-        the fact costs more HBM traffic than re-reading the inputs (C4 shape: 110 us of scaling vs a ~60 us forward).
+        the fact costs more HBM traffic than re-reading the inputs (C4 shape: 110 us of scaling vs a ~60 us forward);
+      * dense NCHW fp32 feature maps (what the reference's FeatExtractor hands over): they are re-laid out channels-last on
+        the way in and their gradients transposed back on the way out; that pass multiplies by the upstream scalar, so
+        the single fused pass runs in forward().
 
     inputs: cfg, pose [B,V,6], K, Kinv, then L target levels, L*V source levels (level-major),
             L depth levels [B,h,w], and L explainability levels [B,>=V,h,w] if cfg.has_expl.
@@ -564,8 +582,13 @@ class FusedPhotoLoss(torch.autograd.Function):
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             raise DvfError("gradients w.r.t. the camera intrinsics are not implemented (unused by the reference)")
         call = _LossCall(cfg, pose, K, Kinv, tensors, ctx.needs_input_grad)
-        ctx.call, ctx.unit_grads = None, None
-        if call.any_grad and not call.any_map_grad:
+        ctx.call, ctx.unit_grads, ctx.relaid = None, None, None
+        if call.any_grad and call.any_map_grad and all(call.relaid) and call.dtype == _lib.F32:
+            # dense NCHW fp32 feature maps: their gradients have to be transposed back anyway, and that pass applies the
+            # upstream scalar for free -- one fused launch here, no forward-only pass
+            terms, ctx.unit_grads = call.run(True)
+            ctx.relaid = call.relaid
+        elif call.any_grad and not call.any_map_grad:
             terms, ctx.unit_grads = call.run(True)
         else:
             terms, _ = call.run(False)
@@ -579,6 +602,11 @@ class FusedPhotoLoss(torch.autograd.Function):
     def backward(ctx, g_loss, _g_terms):
         if ctx.call is not None:
             _, grads = ctx.call.run(True, upstream=g_loss)
+        elif ctx.relaid is not None:
+            n_maps = len(ctx.relaid)
+            maps = [_nhwc_to_nchw_scaled(g, g_loss) for g in ctx.unit_grads[1:1 + n_maps]]
+            rest = _scaled([ctx.unit_grads[0]] + list(ctx.unit_grads[1 + n_maps:]), g_loss)
+            grads = [rest[0]] + maps + rest[1:]
         else:
             grads = _scaled(ctx.unit_grads, g_loss)
         return (None, grads[0], None, None) + tuple(grads[1:])

@@ -249,6 +249,11 @@ int dvf_area_downsample(const float* img /*[BC,H,W]*/, int32_t BC, int32_t H, in
 int dvf_transpose_planes(const void* src /*[B,R,S]*/, void* dst /*[B,S,R]*/, int32_t B, int32_t R, int32_t S,
                          int32_t elem_bytes, void* stream);
 
+/* The same transpose for fp32 with every element multiplied by *scale (device scalar, nullable = 1): the gradient maps
+ * of the feature loss go back to dense NCHW and take the upstream gradient in one pass.                              */
+int dvf_transpose_planes_scaled(const float* src /*[B,R,S]*/, float* dst /*[B,S,R]*/, int32_t B, int32_t R, int32_t S,
+                                const float* scale, void* stream);
+
 /* ---- regularisers next to the path -----------------------
  * smooth_loss (loss_functions.py:23-41, loss_functions_sfm.py:59-77) and explainability_loss
  * (loss_functions_sfm.py:49-56), every scale in ONE launch, value and gradient together.
