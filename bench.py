@@ -331,7 +331,8 @@ def build_steps(wl, B, Bg, host, dev, sets, pdl, peers=None, rank=0):
         pose, K, Kinv = roll(host["pose"]), roll(host["K"]), roll(host["Kinv"])
         expl = [roll(x) for x in host["expl"]] if wl["expl"] else None
         plans = [FusedLossPlan(tgt_pyr, [[sp[l] for sp in src_pyrs] for l in range(L)], [roll(x) for x in host["depths"]],
-                               pose, K, Kinv, expl_levels=expl, downscales=ds, global_batch=Bg, pdl=pdl, **peer_kw(0, L * V, k))]
+                               pose, K, Kinv, expl_levels=expl, downscales=ds, global_batch=Bg, pdl=pdl,
+                               pdl_chained=pdl and not wl.get("feature"), **peer_kw(0, L * V, k))]
         f = wl.get("feature")
         if f:
             cl = lambda t: roll(t).to(torch.bfloat16 if f["dtype"] == "bf16" else torch.float32).contiguous(   # noqa: E731
@@ -720,7 +721,8 @@ def run_b200(args):
                                f"projection, warp + loss + all gradients over all levels and views, pose backward); CUDA graphs of "
                                f"{args.graph_steps} consecutive steps" + ("" if (args.no_pdl or args.sets < 2) else
                                "; consecutive steps work on disjoint input sets and are chained by programmatic dependent launch "
-                               "(DVF_FLAG_PDL): the serial tail of step i overlaps the pixel work of step i+1"),
+                               "(DVF_FLAG_PDL | DVF_FLAG_PDL_CHAINED): step i+1's CTAs start on the SM slots step i leaves or frees, "
+                               "grids sized for overlap (~64 units per CTA)"),
                        "exchange": main["exchange"], "exchange_check_rel_err": main["exchange_check_rel_err"]},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": main["gpu_launches"], "warped_px_per_step_per_gpu": main["warped_px_per_step_per_gpu"],

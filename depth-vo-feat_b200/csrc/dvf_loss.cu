@@ -63,7 +63,9 @@ static int make_plan(const dvf_loss_desc* d, const dvf_level* levels, Plan& pl) 
     // A unit of the channels-last kernel is C/kVec times more work again, so its pieces cost less than one unit.
     // round 2 (programmatic dependent launch, cheaper pieces), C2: 3 -> 53.8 us, 4 -> 52.2, 5 -> 51.4, 6 -> 51.4, 8 -> 51.6,
     // 10 -> 52.0; V = 2 (C3 / C5loss shapes) is flat between 2 and 6.
-    const int by_views = d->V == 1 ? 5 : (d->V == 2 ? 3 : 2);
+    // chained launches (DVF_FLAG_PDL_CHAINED, smaller grids): 3 -> 49.6, 4 -> 48.9, 5 -> 49.3, 6 -> 49.7.
+    const bool chained = (d->flags & DVF_FLAG_PDL) && (d->flags & DVF_FLAG_PDL_CHAINED);
+    const int by_views = d->V == 1 ? (chained ? 4 : 5) : (d->V == 2 ? 3 : 2);
     pl.piece_overhead = d->piece_overhead > 0 ? d->piece_overhead : (d->layout == DVF_NHWC ? 0 : by_views);
   }
   long long per_image = 0;
@@ -188,7 +190,7 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     prm.peer_terms[q] = q < d->n_peers ? d->peer_terms[q] : nullptr;
     if (q < d->n_peers && (!prm.peer_terms[q] || !aligned(prm.peer_terms[q], 4))) return DVF_EINVAL_NULL;
   }
-  prm.pdl = (d->flags & DVF_FLAG_PDL) ? 1 : 0;
+  prm.pdl = (d->flags & DVF_FLAG_PDL) ? ((d->flags & DVF_FLAG_PDL_CHAINED) ? 2 : 1) : 0;
   if (d->grad_dtype != DVF_F32 && !(d->grad_dtype == DVF_BF16 && nhwc && bf16)) return DVF_EUNSUPPORTED;
   prm.grad_bf16 = d->grad_dtype == DVF_BF16;
   bool need_grad = false;

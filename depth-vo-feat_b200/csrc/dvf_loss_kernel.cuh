@@ -87,7 +87,7 @@ struct LossParams {
   int mean_batch;          // batch size in the denominators (>= B: this launch may hold a shard of a larger batch)
   int ctas_per_sm;         // > 0: grid override of the balanced kernels (tuning)
   int grad_bf16;           // NHWC bf16 maps: map gradients are bf16
-  int pdl;                 // programmatic dependent launch (DVF_FLAG_PDL)
+  int pdl;                 // programmatic dependent launch: 1 = DVF_FLAG_PDL, 2 = also DVF_FLAG_PDL_CHAINED
   // producer glue folded into the kernel (dvf_loss_desc): `depth` holds disparities, depth = 1 / (disp + disp_eps)
   // (unsupervise.py:99, train.py:188) and gdepth receives d/d disparity; images are multiplied by img_scale on load
   // (unsupervise.py:101: 0.004 * img)
@@ -1021,7 +1021,25 @@ inline void launch_balanced(const LossParams& prm_in, int cap, cudaStream_t st) 
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kKernel, kLossThreads, 0) != cudaSuccess || n < 1) n = 1;
     per_sm = n;
   }
-  long long g = (long long)(prm.ctas_per_sm > 0 ? prm.ctas_per_sm : per_sm) * num_sms();
+  int use = prm.ctas_per_sm > 0 ? prm.ctas_per_sm : per_sm;
+  if (prm.pdl > 1 && prm.ctas_per_sm <= 0) {
+    // DVF_FLAG_PDL_CHAINED: consecutive launches overlap, so ONE launch need not fill every SM slot -- the slots it
+    // leaves free are taken by its neighbours in the stream.  Fewer, larger CTAs mean fewer pieces (every CTA boundary cuts
+    // one) and less fixed cost: about 64 units per CTA.  Measured, C2 (19 k units): 4 / 3 / 2 / 1 CTAs per SM -> 51.4 / 49.4 /
+    // 48.7 / 48.8 us per step; a C3 shard of 32 images (9 k units): 58.0 / 56.1 / 54.9 / 54.3; C3 with 256 images: flat.
+    const long long want = ((long long)prm.total_units + 64ll * num_sms() - 1) / (64ll * num_sms());
+    use = (int)(want < 1 ? 1 : (want > per_sm ? per_sm : want));
+  }
+  long long g = (long long)use * num_sms();
+  if (prm.pdl > 1 && prm.ctas_per_sm == 0) {
+    // ... and a grid that is a multiple of the batch puts every CTA boundary on an image boundary or inside ONE image: no
+    // CTA walks two images (the pose / intrinsics prologue runs once per CTA) and fewer pieces are cut.  Only while the grid
+    // stays well above the SM count (C2: 296 -> 256 CTAs 48.7 -> 48.4 us; C3, 256 images: 592 -> 512 CTAs 415 -> 402 us; a
+    // 32-image shard would drop to 128 CTAs and lose 7 %: left alone).
+    const long long k = g / prm.B;
+    if (k >= 1 && k * prm.B >= (3ll * num_sms()) / 2) g = k * prm.B;
+  }
+  if (prm.ctas_per_sm < 0) g = -(long long)prm.ctas_per_sm;   // tuning: explicit grid
   if (g > cap) g = cap;
   if (g > prm.total_units) g = prm.total_units;
   prm.grid = (int)g;

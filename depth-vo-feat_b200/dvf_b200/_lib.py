@@ -17,7 +17,7 @@ F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
 PADDING = {"zeros": 0, "border": 1}
 ROTATION = {"euler": 0, "quat": 1}
-FLAG_ALIGN_CORNERS, FLAG_ZERO_GSRC, FLAG_NAN_CHECK, FLAG_NO_TMA, FLAG_PDL, FLAG_DISPARITY = 1, 2, 4, 8, 16, 32
+FLAG_ALIGN_CORNERS, FLAG_ZERO_GSRC, FLAG_NAN_CHECK, FLAG_NO_TMA, FLAG_PDL, FLAG_DISPARITY, FLAG_PDL_CHAINED = 1, 2, 4, 8, 16, 32, 64
 ABI_VERSION = 2
 
 

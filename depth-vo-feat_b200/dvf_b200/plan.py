@@ -26,7 +26,7 @@ class FusedLossPlan:
                  rotation_mode: str = "euler", padding_mode: str = "zeros", need_grad: bool = True,
                  map_grads: bool = False, global_batch: Optional[int] = None, align_corners: bool = False,
                  upstream: Optional[torch.Tensor] = None, fused_pose: bool = True, use_tma: bool = True,
-                 piece_overhead: int = 0, ctas_per_sm: int = 0, pdl: bool = False,
+                 piece_overhead: int = 0, ctas_per_sm: int = 0, pdl: bool = False, pdl_chained: bool = False,
                  peer_terms: Optional[Sequence[int]] = None, peer_rank: int = 0, bf16_grads: bool = True,
                  disparity_eps: Optional[float] = None, img_scale: float = 1.0):
         """Maps: dense NCHW fp32 (images, any C) or channels-last fp32 / bf16 feature maps ([B,C,H,W] tensors in
@@ -34,6 +34,7 @@ class FusedLossPlan:
         global_batch: this plan holds B of the global_batch images of a sharded batch (dvf_loss_desc.mean_batch).
         upstream: device scalar multiplying every gradient (dvf_loss_desc.upstream).
         pdl: programmatic dependent launch (DVF_FLAG_PDL): back-to-back launches of plans with DISJOINT buffers overlap.
+        pdl_chained: this plan is launched in a chain of such launches (DVF_FLAG_PDL_CHAINED): grid sized for overlap.
         peer_terms: device pointers (as mapped in this process) of every rank's [n_peers][L*V] exchange buffer; the kernel
         epilogue stores this rank's loss terms into row peer_rank of each (dvf_b200.dist.PeerTerms)."""
         from .ops import _nhwc_ok
@@ -92,7 +93,8 @@ class FusedLossPlan:
                     for v in range(V):
                         lv.gsrc[v] = self.gsrc[l][v].data_ptr()
         flags = (_lib.FLAG_ALIGN_CORNERS if align_corners else 0) | (_lib.FLAG_ZERO_GSRC if self.map_grads else 0) | \
-                (0 if use_tma else _lib.FLAG_NO_TMA) | (_lib.FLAG_PDL if pdl else 0)
+                (0 if use_tma else _lib.FLAG_NO_TMA) | (_lib.FLAG_PDL if pdl else 0) | \
+                (_lib.FLAG_PDL_CHAINED if (pdl and pdl_chained) else 0)
         self.desc = dvf_loss_desc(B, Cc, V, L, dtype, layout, PADDING[padding_mode], flags, int(global_batch or 0), _lib.BF16 if self.grad_bf16 else _lib.F32,
                                   int(piece_overhead), int(ctas_per_sm), None if upstream is None else upstream.data_ptr(), None,
                                   0, 0, None, float(disparity_eps or 0.0), float(img_scale))

@@ -83,7 +83,13 @@ typedef enum dvf_flags {
    * DISPARITY; the kernel uses depth = 1 / (disp + dvf_loss_desc.disp_eps) -- `1/(inv_depth+1e-4)` of
    * unsupervise.py:99, `1/disp` of train.py:188 (eps 0) -- evaluated as torch does (rounded add, reciprocal), and
    * dvf_level.gdepth receives d/d disparity = -g_depth * depth^2.                                              */
-  DVF_FLAG_DISPARITY = 32
+  DVF_FLAG_DISPARITY = 32,
+  /* with DVF_FLAG_PDL: the caller promises that this launch sits in a CHAIN of such launches issued back to back
+   * (consecutive steps / micro-batches of a captured graph).  The grid is then sized for overlap instead of for the
+   * whole GPU -- about 64 units of 256 pixels per CTA, down to one CTA per SM: fewer CTA boundaries = fewer pieces =
+   * less fixed cost, and the SM slots one launch leaves free are filled by its neighbours in the stream (C2: 51.4 ->
+   * 48.7 us per step).  Sums over CTAs are folded in another order than without the flag (same 1e-7 class).      */
+  DVF_FLAG_PDL_CHAINED = 64
 } dvf_flags;
 
 /* Image-tensor descriptor shared by the warp and loss entries. */
@@ -189,7 +195,8 @@ typedef struct dvf_loss_desc {
   int32_t grad_dtype;     /* dvf_dtype of gtgt: DVF_F32, or DVF_BF16 for NHWC bf16 maps (gsrc is accumulated
                              and therefore always fp32)                                            */
   int32_t piece_overhead; /* tuning: fixed cost of an (image, level) piece in 256-px units; <= 0 = default */
-  int32_t ctas_per_sm;    /* tuning: resident CTAs per SM of the image kernel's grid; <= 0 = occupancy query */
+  int32_t ctas_per_sm;    /* tuning: resident CTAs per SM of the balanced kernels' grid; 0 = automatic, < 0 = a grid of
+                             exactly -ctas_per_sm CTAs                                               */
   const float* upstream;  /* device scalar g = d(total)/d(sum of terms): every gradient is scaled by it
                              (terms are not); NULL = 1                                              */
   int32_t* nan_flags;     /* device word for DVF_FLAG_NAN_CHECK, OR-ed into (never cleared); nullable */

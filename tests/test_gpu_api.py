@@ -171,6 +171,25 @@ def test_pdl_chain_is_bit_identical(ops, syn, V, with_expl):
         assert all(np.array_equal(a, b) for a, b in zip(_snapshot(p), w)), "captured PDL chain differs from the plain launch"
 
 
+def test_pdl_chained_small_grid(ops, syn):
+    """DVF_FLAG_PDL_CHAINED: grid sized for overlap (fewer, larger CTAs).  Per-pixel outputs stay bit-identical; sums over CTAs
+    are folded in another order (1e-6)."""
+    B, H, W, L, V, S = 6, 64, 208, 3, 2, 3
+    plain = _plans(ops, syn, B, H, W, L, V, S, True)
+    chained = _plans(ops, syn, B, H, W, L, V, S, True, pdl=True, pdl_chained=True)
+    for p in plain:
+        p.launch()
+    for _ in range(3):
+        for p in chained:
+            p.launch()
+    torch.cuda.synchronize()
+    for p, q in zip(plain, chained):
+        assert_close(npy(q.terms), npy(p.terms), tol=1e-6, what="terms")
+        assert_close(npy(q.gpose), npy(p.gpose), tol=1e-6, what="gpose")
+        for a, b in zip(p.gdepth + p.gexpl, q.gdepth + q.gexpl):
+            assert np.array_equal(npy(a), npy(b)), "per-pixel gradients do not depend on the grid"
+
+
 def test_upstream_scalar_and_sharded_mean(ops, syn):
     """dvf_loss_desc.upstream scales every gradient (not the terms); mean_batch makes a shard return its share of the
     global mean, so that shards add up to the un-sharded call (dvf_b200.dist)."""
