@@ -173,8 +173,9 @@ def pose_proj_fwd(vec, K, Kinv, V, rotation_mode, downscales: Sequence[float], w
     P = torch.empty(L, n, 3, 4, device=dev, dtype=torch.float32) if (K is not None and L) else None
     Ks = torch.empty(L, B, 3, 3, device=dev, dtype=torch.float32) if (Kinv is not None and L) else None
     ds = (C.c_float * max(L, 1))(*[float(d) for d in downscales])
-    _lib.check(lib.dvf_pose_proj_fwd(_ptr(vec), _ptr(K), _ptr(Kinv), B, V, ROTATION[rotation_mode], ds, L,
-                                     _ptr(posemat), _ptr(P), _ptr(Ks), _stream()), "dvf_pose_proj_fwd")
+    with _same_device(vec, K, Kinv):
+        _lib.check(lib.dvf_pose_proj_fwd(_ptr(vec), _ptr(K), _ptr(Kinv), B, V, ROTATION[rotation_mode], ds, L,
+                                         _ptr(posemat), _ptr(P), _ptr(Ks), _stream()), "dvf_pose_proj_fwd")
     return posemat, P, Ks
 
 
@@ -184,8 +185,9 @@ def pose_proj_bwd(gP, gposemat, vec, K, V, rotation_mode, downscales: Sequence[f
     L = len(downscales)
     gvec = torch.empty(n, 6, device=vec.device, dtype=torch.float32)
     ds = (C.c_float * max(L, 1))(*[float(d) for d in downscales])
-    _lib.check(lib.dvf_pose_proj_bwd(_ptr(gP), _ptr(gposemat), _ptr(vec), _ptr(K), n // V, V, ROTATION[rotation_mode],
-                                     ds, L, _ptr(gvec), _stream()), "dvf_pose_proj_bwd")
+    with _same_device(gP, gposemat, vec, K):
+        _lib.check(lib.dvf_pose_proj_bwd(_ptr(gP), _ptr(gposemat), _ptr(vec), _ptr(K), n // V, V, ROTATION[rotation_mode],
+                                         ds, L, _ptr(gvec), _stream()), "dvf_pose_proj_bwd")
     return gvec
 
 
@@ -231,8 +233,9 @@ def inverse_warp_fwd_P(img, depth, P, Kinv, padding_mode="zeros", want_valid=Fal
     warped = torch.empty_like(img)
     valid = torch.empty(depth.shape, dtype=torch.uint8, device=img.device) if want_valid else None
     d = _desc(img, padding_mode)
-    _lib.check(lib.dvf_inverse_warp_fwd(C.byref(d), _ptr(img), _ptr(depth), _ptr(P), _ptr(Kinv), _ptr(warped),
-                                        _ptr(valid), _stream()), "dvf_inverse_warp_fwd")
+    with _same_device(img, depth, P, Kinv):
+        _lib.check(lib.dvf_inverse_warp_fwd(C.byref(d), _ptr(img), _ptr(depth), _ptr(P), _ptr(Kinv), _ptr(warped),
+                                            _ptr(valid), _stream()), "dvf_inverse_warp_fwd")
     return (warped, valid) if want_valid else warped
 
 
@@ -246,10 +249,11 @@ def inverse_warp_bwd_P(gout, img, depth, P, Kinv, padding_mode="zeros", need_gim
     gP = torch.empty(img.shape[0], 3, 4, device=img.device, dtype=torch.float32)
     gimg = torch.zeros_like(img) if need_gimg else None
     nbytes = lib.dvf_inverse_warp_bwd_workspace_bytes(C.byref(d))
-    ws = workspace(nbytes, img.device, ('warp_bwd',) + tuple(img.shape))
-    _lib.check(lib.dvf_inverse_warp_bwd(C.byref(d), _ptr(gout), _ptr(img), _ptr(depth), _ptr(P), _ptr(Kinv),
-                                        _ptr(gdepth), _ptr(gP), _ptr(gimg), _ptr(ws), ws.numel(), _stream()),
-               "dvf_inverse_warp_bwd")
+    with _same_device(gout, img, depth, P, Kinv):
+        ws = workspace(nbytes, img.device, ('warp_bwd',) + tuple(img.shape))
+        _checked(lib.dvf_inverse_warp_bwd(C.byref(d), _ptr(gout), _ptr(img), _ptr(depth), _ptr(P), _ptr(Kinv),
+                                          _ptr(gdepth), _ptr(gP), _ptr(gimg), _ptr(ws), ws.numel(), _stream()),
+                 "dvf_inverse_warp_bwd", ws)
     return gimg, gdepth, gP
 
 

@@ -33,9 +33,11 @@ def test_dropin_signatures_match_reference():
         ("intrinsics_inv", E), ("rotation_mode", "euler"), ("padding_mode", "zeros")]
     assert params(lf.smooth_loss) == [("pred_map", E), ("scale_factor", 1)]
     # loss_functions_sfm.py:9
-    assert params(sfm.photometric_reconstruction_loss) == [
+    # (the reference's nine parameters, then keyword-only-in-practice extensions with defaults that keep its behaviour)
+    assert params(sfm.photometric_reconstruction_loss)[:9] == [
         ("tgt_img", E), ("ref_imgs", E), ("intrinsics", E), ("intrinsics_inv", E), ("depth", E),
         ("explainability_mask", E), ("pose", E), ("rotation_mode", "euler"), ("padding_mode", "zeros")]
+    assert params(sfm.photometric_reconstruction_loss)[9:] == [("disparity_eps", None)]
     for name in ("explainability_loss", "smooth_loss", "compute_errors", "inverse_warp"):
         assert hasattr(sfm, name)
     # loss_function_sfm_old.py:7
