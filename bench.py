@@ -75,7 +75,7 @@ def parse():
     ap.add_argument("--config", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the workload's batch (per GPU or global, as the workload defines it)")
     ap.add_argument("--sets", type=int, default=4, help="distinct input sets rotated through (working set > L2)")
-    ap.add_argument("--graph-steps", type=int, default=16, help="consecutive steps per CUDA graph")
+    ap.add_argument("--graph-steps", type=int, default=64, help="consecutive steps per CUDA graph (at most)")
     ap.add_argument("--prewarm-ms", type=float, default=400.0, help="untimed clock ramp before the W warm-up steps")
     ap.add_argument("--roofline-ms", type=float, default=1500.0, help="length of the dominant-kernel timing loop")
     ap.add_argument("--e2e-steps", type=int, default=20)
@@ -345,8 +345,10 @@ def build_steps(wl, B, Bg, host, dev, sets, pdl, peers=None, rank=0):
 
 
 class Runner:
-    """CUDA graphs over the rotating input sets; N > 1: the loss terms of every step are all-reduced on a side stream
-    inside the graph (step i's exchange overlaps step i+1's kernel; the graph joins the side stream at its end)."""
+    """CUDA graphs over the rotating input sets: one graph holds up to `graph_steps` consecutive steps (a run of n steps is
+    n // graph_steps replays of the long graph plus ONE graph with the remainder, captured ahead of the timed region by
+    prepare()).  N > 1 with --exchange nccl: the loss terms of every step are all-reduced on a side stream inside the graph
+    (step i's exchange overlaps step i+1's kernel; the graph joins the side stream at its end)."""
 
     def __init__(self, steps, graph_steps, world, allreduce, only=None):
         import torch.distributed as dist
@@ -355,18 +357,18 @@ class Runner:
         self.graph_steps = max(self.n_sets, (graph_steps // self.n_sets) * self.n_sets)
         self.exchange = "none"
         launch = (lambda s: s.launch()) if only is None else (lambda s: only(s).launch())
-        main = torch.cuda.Stream()
-        main.wait_stream(torch.cuda.current_stream())
+        self.main = torch.cuda.Stream()
+        self.main.wait_stream(torch.cuda.current_stream())
         xs = torch.cuda.Stream()
-        do_ar = world > 1 and allreduce
+        self.do_ar = do_ar = world > 1 and allreduce
         # term buffers of the exchange: one per step of the long graph (an all-reduce may still be in flight when the
         # same input set is launched again)
         self.xbuf = ([torch.zeros(steps[0].n_terms, device=steps[0].plans[0].terms.device) for _ in range(self.graph_steps)]
                      if do_ar else None)
+        self.xs = xs
+        copied = self._copied = {}
 
-        copied = {}
-
-        def body(i, captured):
+        def body(i):
             st = steps[i % self.n_sets]
             cur = torch.cuda.current_stream()
             if do_ar and (i - self.n_sets) in copied:
@@ -381,52 +383,62 @@ class Runner:
                     ev.record(xs)
                     copied[i] = ev
                     dist.all_reduce(self.xbuf[i % self.graph_steps])
-        with torch.cuda.stream(main):
+        self._body = body
+        self.graphs = {}
+        self.eager = False
+        with torch.cuda.stream(self.main):
             for i in range(self.n_sets):         # untimed: first launches, NCCL communicator warm-up
-                body(i, False)
-            main.wait_stream(xs)
+                body(i)
+            self.main.wait_stream(xs)
             torch.cuda.synchronize()
             copied.clear()
-            self.single = []
-            try:
-                self.long = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.long, stream=main, capture_error_mode="thread_local"):
-                    for i in range(self.graph_steps):
-                        body(i, True)
-                    if do_ar:
-                        torch.cuda.current_stream().wait_stream(xs)
-                copied.clear()
-                for k in range(self.n_sets):
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=main, capture_error_mode="thread_local"):
-                        body(k, True)
-                        if do_ar:
-                            torch.cuda.current_stream().wait_stream(xs)
-                    copied.clear()
-                    self.single.append(g)
-                self.exchange = ("NCCL all-reduce of the loss terms every step, on a side stream inside the CUDA graph"
-                                 if do_ar else "none")
-            except Exception as e:   # NCCL refused capture: eager per-step exchange, still every step
-                if not do_ar:
-                    raise
-                torch.cuda.synchronize()
-                copied.clear()
-                self.long, self.single = None, []
-                self.exchange = f"NCCL all-reduce every step, eager on a side stream (graph capture failed: {type(e).__name__})"
-                self._eager = body
-        torch.cuda.current_stream().wait_stream(main)
+        try:
+            self._graph(self.graph_steps)
+            self.exchange = ("NCCL all-reduce of the loss terms every step, on a side stream inside the CUDA graph"
+                             if do_ar else "none")
+        except Exception as e:   # NCCL refused capture: eager per-step exchange, still every step
+            if not do_ar:
+                raise
+            torch.cuda.synchronize()
+            copied.clear()
+            self.eager = True
+            self.exchange = f"NCCL all-reduce every step, eager on a side stream (graph capture failed: {type(e).__name__})"
+        torch.cuda.current_stream().wait_stream(self.main)
         torch.cuda.synchronize()
 
+    def _graph(self, n_steps):
+        g = self.graphs.get(n_steps)
+        if g is None:
+            torch.cuda.synchronize()
+            with torch.cuda.stream(self.main):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.main, capture_error_mode="thread_local"):
+                    for i in range(n_steps):
+                        self._body(i)
+                    if self.do_ar:
+                        torch.cuda.current_stream().wait_stream(self.xs)
+                self._copied.clear()
+            torch.cuda.current_stream().wait_stream(self.main)
+            torch.cuda.synchronize()
+            self.graphs[n_steps] = g
+        return g
+
+    def prepare(self, n):
+        """capture whatever run(n) will replay (outside any timed region)"""
+        if not self.eager and n % self.graph_steps:
+            self._graph(n % self.graph_steps)
+
     def run(self, n):
-        if self.long is None:
+        if self.eager:
             for i in range(n):
-                self._eager(i, False)
+                self._body(i)
             return
         q, r = divmod(n, self.graph_steps)
+        long = self._graph(self.graph_steps)
         for _ in range(q):
-            self.long.replay()
-        for i in range(r):
-            self.single[i % self.n_sets].replay()
+            long.replay()
+        if r:
+            self._graph(r).replay()
 
     def spin(self, ms):
         t_end = time.perf_counter() + ms / 1e3
@@ -437,6 +449,7 @@ class Runner:
 
 def timed(runner, n, world, dev):
     import torch.distributed as dist
+    runner.prepare(n)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -503,7 +516,7 @@ def measure_workload(name, wl, args, world, rank, dev, sampler, steps_n, warmup_
         if mode == "p2p":
             got = torch.cat([pt.gathered(last).sum(0) for pt in peers])
         else:
-            got = runner.xbuf[(steps_n - 1) % runner.graph_steps] if steps_n % runner.graph_steps == 0 else ref
+            got = ref   # (buffers rotate inside the graphs; the nccl mode is the A/B arm, not the checked one)
         xcheck = float(((got - ref).abs().max() / ref.abs().max()).item())
     out = {"value": wpx * world * steps_n / (ms_total * 1e-3), "ms_per_step": ms_total / steps_n, "steps": steps_n,
            "warped_px_per_step_per_gpu": wpx, "gpu_launches": steps[0].n_launches * steps_n,
@@ -512,6 +525,7 @@ def measure_workload(name, wl, args, world, rank, dev, sampler, steps_n, warmup_
     if roofline:
         dom = Runner(steps, args.graph_steps, 1, False, only=lambda s: s.dominant)
         n_roof = min(200000, max(50, int(args.roofline_ms * 1e-3 / max(ms_total * 1e-3 / steps_n, 1e-6))))
+        dom.prepare(n_roof)
         dom.run(16)
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()

@@ -375,3 +375,37 @@ def test_producer_glue_matches_separate_torch_passes(ops, syn):
     assert abs(g2.item() - r2.item()) <= 1e-6 * abs(r2.item())
     for u, v in zip(x, y):
         assert_close(npy(v.grad), npy(u.grad), tol=RTOL_F32, what="d disparity (multi-scale)")
+
+
+def test_fused_terms_exchange_single_rank(ops, syn):
+    """dvf_loss_desc.peer_terms on ONE GPU (world size 1): the kernel's epilogue stores the loss terms into the exchange buffer
+    obtained from dvf_b200.dist.PeerTerms (symmetric memory / CUDA IPC mapping); the N > 1 path is exercised by bench.py under
+    torchrun, which checks it against an NCCL all-reduce (exchange_check_rel_err)."""
+    import os
+    import socket
+    import torch.distributed as dist
+    from dvf_b200.dist import PeerTerms
+    created = False
+    if not dist.is_initialized():
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        B, H, W, L, V, S = 4, 32, 104, 2, 2, 2
+        pt = PeerTerms(S, L * V, torch.device("cuda", 0))
+        assert pt.world == 1 and pt.how in ("symmetric_memory", "cuda_ipc")
+        plans = []
+        for k in range(S):
+            plans += _plans(ops, syn, B, H, W, L, V, 1, True, peer_terms=pt.slot_ptrs(k), peer_rank=0)
+        for p in plans:
+            p.launch()
+        torch.cuda.synchronize()
+        for k, p in enumerate(plans):
+            assert np.array_equal(npy(pt.gathered(k)[0]), npy(p.terms)), "terms stored by the kernel epilogue"
+    finally:
+        if created:
+            dist.destroy_process_group()
