@@ -296,6 +296,7 @@ class Step:
         self.n_launches = sum(p.n_launches for p in plans)
         self.dominant = max(plans, key=lambda p: p.algorithmic_bytes())
         self.n_terms = sum(p.terms.numel() for p in plans)
+        self.chained = all(bool(p.desc.flags & 64) for p in plans)   # DVF_FLAG_PDL_CHAINED
 
     def copy_terms_into(self, buf):
         o = 0
@@ -303,8 +304,12 @@ class Step:
             buf[o:o + p.terms.numel()].copy_(p.terms)
             o += p.terms.numel()
 
-    def launch(self):
+    def launch(self, edge=False):
+        """edge: first or last step of a chain of dependent launches -- nobody to overlap with on one side, so the launch takes
+        the full grid (the others are sized for overlap, DVF_FLAG_PDL_CHAINED)"""
         for p in self.plans:
+            if self.chained:
+                p.set_chained(not edge)
             p.launch()
 
 
@@ -356,7 +361,14 @@ class Runner:
         self.n_sets = len(steps)
         self.graph_steps = max(self.n_sets, (graph_steps // self.n_sets) * self.n_sets)
         self.exchange = "none"
-        launch = (lambda s: s.launch()) if only is None else (lambda s: only(s).launch())
+        def launch(s, edge):
+            if only is None:
+                s.launch(edge)
+                return
+            p = only(s)
+            if s.chained:
+                p.set_chained(not edge)
+            p.launch()
         self.main = torch.cuda.Stream()
         self.main.wait_stream(torch.cuda.current_stream())
         xs = torch.cuda.Stream()
@@ -368,12 +380,12 @@ class Runner:
         self.xs = xs
         copied = self._copied = {}
 
-        def body(i):
+        def body(i, edge=False):
             st = steps[i % self.n_sets]
             cur = torch.cuda.current_stream()
             if do_ar and (i - self.n_sets) in copied:
                 cur.wait_event(copied.pop(i - self.n_sets))   # this input set's terms have left for the exchange
-            launch(st)
+            launch(st, edge)
             if do_ar:
                 # copy + all-reduce on the side stream: the loss kernels stay back to back on the main stream
                 xs.wait_stream(cur)
@@ -414,7 +426,7 @@ class Runner:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self.main, capture_error_mode="thread_local"):
                     for i in range(n_steps):
-                        self._body(i)
+                        self._body(i, i == 0 or i == n_steps - 1)
                     if self.do_ar:
                         torch.cuda.current_stream().wait_stream(self.xs)
                 self._copied.clear()

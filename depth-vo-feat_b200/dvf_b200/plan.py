@@ -132,6 +132,15 @@ class FusedLossPlan:
                                               self.rotation, self.ds, self.L, self.gpose.data_ptr(), stream),
                    "dvf_pose_proj_bwd")
 
+    def set_chained(self, chained: bool):
+        """switch DVF_FLAG_PDL_CHAINED for the following launches (a chain's first and last launch have no neighbour on one
+        side: with the full grid they ramp the GPU up and down faster)"""
+        if self.desc.flags & _lib.FLAG_PDL:
+            if chained:
+                self.desc.flags |= _lib.FLAG_PDL_CHAINED
+            else:
+                self.desc.flags &= ~_lib.FLAG_PDL_CHAINED
+
     def launch_fused(self, stream: int):
         """ONE launch: pose_vec2mat + projection, warp + loss + all gradients, pose backward."""
         _lib.check(self.lib.dvf_photo_loss_fused_pose(C.byref(self.desc), self.levels, C.byref(self.pose_args),
