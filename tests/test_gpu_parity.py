@@ -892,3 +892,37 @@ def test_caffe_edge_aware_smoothness_vs_oracle(ops, oracle):
         out.backward()
         assert abs(out.item() - 10.0 * loss.sum()) <= 2e-6 * 10.0 * loss.sum()
         assert_close(npy(d.grad), g, tol=2e-6, what=f"d inv_depth {N}x{H}x{W}")
+
+
+def test_caffe_two_view_batch_concatenated_form(ops, syn):
+    """experiments/depth_odometry/train.prototxt:4309-4437: the stereo and the temporal view concatenated along the batch
+    axis go through the geometry layers in one pass; the result equals two separate single-view passes (values and
+    gradients; parity of the layer family itself is unpinned)."""
+    import geo_transform as gt
+    import se3_generate
+    N, H, W = 3, 40, 128
+    g = torch.Generator().manual_seed(4)
+    inv = (torch.rand(N, 1, H, W, generator=g) * 0.3 + 0.02).cuda()
+    T_s = torch.tensor([0.0, 0.0, 0.0, 0.5, 0.0, 0.0]).view(1, 6, 1, 1).repeat(N, 1, 1, 1).cuda()
+    T_t = (torch.randn(N, 6, 1, 1, generator=g) * torch.tensor([0.01, 0.01, 0.01, 0.05, 0.02, 0.3]).view(1, 6, 1, 1)).cuda()
+    K = torch.tensor([0.58 * W, 1.92 * H, 0.49 * W, 0.49 * H]).view(1, 4, 1, 1).repeat(N, 1, 1, 1).cuda()
+    L2, R1, R2 = [torch.rand(N, 3, H, W, generator=g).cuda() for _ in range(3)]
+
+    def single(T, src, d):
+        SE3 = se3_generate.generate_se3(T)
+        depth = (d + 1e-4).pow(-1)
+        proj = gt.pin_hole_project(gt.geo_transform(depth, SE3, K), K)
+        return gt.abs_loss(gt.inverse_warp(src, proj), R2)
+
+    a = inv.clone().requires_grad_(True)
+    ta, tb = T_s.clone().requires_grad_(True), T_t.clone().requires_grad_(True)
+    e_lr, e_r12 = gt.two_view_warp_errors(a, ta, tb, K, L2, R1, R2)
+    (e_lr + e_r12).backward()
+    b = inv.clone().requires_grad_(True)
+    sa, sb = T_s.clone().requires_grad_(True), T_t.clone().requires_grad_(True)
+    r_lr, r_r12 = single(sa, L2, b), single(sb, R1, b)
+    (r_lr + r_r12).backward()
+    assert abs(e_lr.item() - r_lr.item()) <= 1e-6 * abs(r_lr.item()) and abs(e_r12.item() - r_r12.item()) <= 1e-6 * abs(r_r12.item())
+    assert_close(npy(a.grad), npy(b.grad), tol=1e-6, what="d inv_depth")
+    assert_close(npy(ta.grad), npy(sa.grad), tol=1e-5, what="d T_R2L")
+    assert_close(npy(tb.grad), npy(sb.grad), tol=1e-5, what="d T_2to1")
