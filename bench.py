@@ -436,9 +436,16 @@ class Runner:
         return g
 
     def prepare(self, n):
-        """capture whatever run(n) will replay (outside any timed region)"""
-        if not self.eager and n % self.graph_steps:
-            self._graph(n % self.graph_steps)
+        """capture whatever run(n) will replay and launch it once (the first launch of a graph uploads it), outside any timed
+        region"""
+        if self.eager:
+            return
+        for k in ({self.graph_steps} if n >= self.graph_steps else set()) | ({n % self.graph_steps} - {0}):
+            fresh = k not in self.graphs
+            g = self._graph(k)
+            if fresh:
+                g.replay()
+                torch.cuda.synchronize()
 
     def run(self, n):
         if self.eager:
@@ -514,6 +521,8 @@ def measure_workload(name, wl, args, world, rank, dev, sampler, steps_n, warmup_
     wpx = steps[0].warped_px
     assert wpx == warped_px(wl, Bl)
     t0 = time.time()
+    runner.prepare(steps_n)          # capture the graphs of the timed region now: the GPU must not idle between warm-up and timing
+    runner.prepare(max(warmup_n, 3))
     runner.spin(args.prewarm_ms)
     runner.run(max(warmup_n, 3))
     ms_total = timed(runner, steps_n, world, dev)
