@@ -97,11 +97,14 @@ def parse():
 # synthetic workload
 # ------------------------------------------------------------------------------------------------
 def local_batch(wl, world, override=0):
+    """(images per rank, global batch); the sharding rule is dvf_b200.dist.shard_range (equal contiguous slices here)"""
+    from dvf_b200.dist import shard_range
     b = override or wl["batch"]
     if wl["batch_is"] == "global":
         if b % world:
             raise SystemExit(f"global batch {b} does not divide over {world} GPUs")
-        return b // world, b
+        lo, hi = shard_range(b, 0, world)
+        return hi - lo, b
     return b, b * world
 
 
