@@ -442,19 +442,20 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
 #endif
   constexpr int kPlanes = 1 + kC + (kExpl ? kV : 0);   // streamed planes per chunk
   // pixel pairs per thread between two ring hand-overs (= CTA barriers).  Measured on C2 with the balanced split:
-  // 2 pairs x 4 stages 69.6 us, 3 x 3 69.4 us, 4 x 2 67.5 us; with masks the stages get too large for more than 1.
-#ifdef DVF_PAIRS_PER_CHUNK   // experiment builds (profiles/ab.sh)
-  constexpr int kPairsPerChunk = kPlanes <= 4 ? DVF_PAIRS_PER_CHUNK : 1;
-#else
-  constexpr int kPairsPerChunk = kPlanes <= 4 ? 4 : 1;
+  // 2 pairs x 4 stages 69.6 us, 3 x 3 69.4 us, 4 x 2 67.5 us; with the masks of up to two views 3 pairs x 2 stages.
+#ifndef DVF_PAIRS_PER_CHUNK   // experiment builds (profiles/ab.sh) override these
+#define DVF_PAIRS_PER_CHUNK 4
 #endif
+#ifndef DVF_PAIRS_PER_CHUNK_MASKS   // 5 or 6 planes (masks of one or two views).  C3 (V = 2 + masks): 1 -> 405 us, 2 -> 400, 3 -> 390
+#define DVF_PAIRS_PER_CHUNK_MASKS 3
+#endif
+  constexpr int kPairsPerChunk = kPlanes <= 4 ? DVF_PAIRS_PER_CHUNK : (kPlanes <= 6 ? DVF_PAIRS_PER_CHUNK_MASKS : 1);
   constexpr int kChunk = kUnitPx * kPairsPerChunk;    // pixels per chunk
   // ring depth: as deep as 40 KB of static shared memory allow (4 CTAs per SM stay resident), at least 2
-#ifdef DVF_RING_BYTES
-  constexpr int kStagesFit = DVF_RING_BYTES / (kPlanes * kChunk * 4);
-#else
-  constexpr int kStagesFit = 40000 / (kPlanes * kChunk * 4);
+#ifndef DVF_RING_BYTES
+#define DVF_RING_BYTES 38000   // 2 stages of 4 planes x 1024 px, or of 6 planes x 768 px
 #endif
+  constexpr int kStagesFit = DVF_RING_BYTES / (kPlanes * kChunk * 4);
   constexpr int kSt = kStagesFit >= kStages ? kStages : (kStagesFit < 2 ? 2 : kStagesFit);
   __shared__ __align__(16) float s_P[kV][12];
   __shared__ __align__(16) float s_M[12];
