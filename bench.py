@@ -84,6 +84,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip strong_c3 / unfused_gpu")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="tuning: dvf_loss_desc.ctas_per_sm of the image-loss plans (0 = automatic)")
     ap.add_argument("--no-pdl", action="store_true", help="plain launches instead of programmatic dependent launches (A/B)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl", "none"],
                     help="N > 1, every step: p2p = the loss kernel stores its terms into every peer's buffer over NVLink (fused "
@@ -316,7 +317,7 @@ class Step:
             p.launch()
 
 
-def build_steps(wl, B, Bg, host, dev, sets, pdl, peers=None, rank=0):
+def build_steps(wl, B, Bg, host, dev, sets, pdl, peers=None, rank=0, ctas_per_sm=0):
     """peers: None, or a list that receives one dvf_b200.dist.PeerTerms per plan of a step (fused exchange of the terms)"""
     from dvf_b200 import ops
     from dvf_b200.plan import FusedLossPlan
@@ -340,7 +341,7 @@ def build_steps(wl, B, Bg, host, dev, sets, pdl, peers=None, rank=0):
         expl = [roll(x) for x in host["expl"]] if wl["expl"] else None
         plans = [FusedLossPlan(tgt_pyr, [[sp[l] for sp in src_pyrs] for l in range(L)], [roll(x) for x in host["depths"]],
                                pose, K, Kinv, expl_levels=expl, downscales=ds, global_batch=Bg, pdl=pdl,
-                               pdl_chained=pdl and not wl.get("feature"), **peer_kw(0, L * V, k))]
+                               pdl_chained=pdl and not wl.get("feature"), ctas_per_sm=ctas_per_sm, **peer_kw(0, L * V, k))]
         f = wl.get("feature")
         if f:
             cl = lambda t: roll(t).to(torch.bfloat16 if f["dtype"] == "bf16" else torch.float32).contiguous(   # noqa: E731
@@ -510,13 +511,13 @@ def measure_workload(name, wl, args, world, rank, dev, sampler, steps_n, warmup_
     if mode == "p2p":
         try:
             peers = []
-            steps = build_steps(wl, Bl, Bg, host, dev, args.sets, pdl, peers=peers, rank=rank)
+            steps = build_steps(wl, Bl, Bg, host, dev, args.sets, pdl, peers=peers, rank=rank, ctas_per_sm=args.ctas_per_sm)
         except RuntimeError as e:
             if "peer-to-peer" not in str(e):
                 raise
             mode, peers = "nccl", None
     if peers is None:
-        steps = build_steps(wl, Bl, Bg, host, dev, args.sets, pdl)
+        steps = build_steps(wl, Bl, Bg, host, dev, args.sets, pdl, ctas_per_sm=args.ctas_per_sm)
     runner = Runner(steps, args.graph_steps, world, mode == "nccl")
     if mode == "p2p":
         runner.exchange = (f"fused into the loss kernel: every step its epilogue stores the rank's loss terms into every peer's buffer "

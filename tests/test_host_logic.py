@@ -102,3 +102,30 @@ def test_synthetic_inputs_are_deterministic():
         assert torch.equal(a[k], b[k])
     assert a["depth"].min() > 3.0 and a["depth"].max() <= 50.0 + 1e-3
     assert float(a["T_R2L"][0, 0]) == pytest.approx(0.53233)
+
+
+def test_bench_reference_arm_line_and_config_objects():
+    """bench.py: both arms describe the workload with the SAME config object; the reference arm runs on the CPU alone and
+    prints one JSON line with the keys the driver reads (tiny batch here: C1 at batch 2, one step)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, repo)
+    import bench
+    for name, wl in bench.WORKLOADS.items():
+        a = type("A", (), dict(batch=0, iid_depth=False))()
+        c1, c8 = bench.config_dict(name, wl, 1, a), bench.config_dict(name, wl, 8, a)
+        assert c1["workload"] == wl["title"] and c1["name"] == name
+        assert c8["global_batch"] == (wl["batch"] if wl["batch_is"] == "global" else wl["batch"] * 8)
+        assert c8["scaling"] == ("strong" if wl["batch_is"] == "global" else "weak")
+        assert bench.warped_px(wl, 2) > 0
+    out = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--config", "C1", "--steps", "1",
+                          "--warmup", "1", "--cpu-batch", "2"], capture_output=True, text=True, timeout=300, cwd=repo)
+    assert out.returncode == 0, out.stderr[-400:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["higher_is_better"] is True
+    assert d["config"] == bench.config_dict("C1", bench.WORKLOADS["C1"], 1, type("A", (), dict(batch=0, iid_depth=False))())
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["gpu_launches"] == 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
