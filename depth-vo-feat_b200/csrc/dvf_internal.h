@@ -35,4 +35,10 @@ inline int num_sms() {
   return n;
 }
 
+// dvf_inverse_warp_bwd without d img, run by the image kernel of the fused loss (dvf_loss.cu): TMA ring, balanced split
+bool warp_bwd_fused_ok(const dvf_desc* d, const void* gout, const void* img, const float* depth);
+size_t warp_bwd_fused_workspace_bytes(const dvf_desc* d);
+int warp_bwd_fused(const dvf_desc* d, const void* gout, const void* img, const float* depth, const float* P, const float* Kinv,
+                   float* gdepth, float* gP, void* workspace, size_t workspace_bytes, void* stream);
+
 }  // namespace dvf

@@ -126,8 +126,9 @@ DVF_EXPORT size_t dvf_photo_loss_workspace_bytes(const dvf_loss_desc* d, const d
   return pl.bytes;
 }
 
+// ext_grad: levels[0].tgt holds d L / d warped and the image kernel runs as the backward of the materialised warp (kExt)
 static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_pose_args* pose, float* terms,
-                    void* workspace, size_t workspace_bytes, void* stream) {
+                    void* workspace, size_t workspace_bytes, void* stream, bool ext_grad = false) {
   Plan pl;
   int st = make_plan(d, levels, pl);
   if (st != DVF_OK) return st;
@@ -294,6 +295,11 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
       if (s.expl) tma = tma && aligned(s.expl, 16) && (s.expl_bstride % 4 == 0);
       for (int v = 0; v < d->V; ++v) tma = tma && aligned(s.src[v], 16);
     }
+    if (ext_grad) {
+      if (!tma || expl || d->V != 1 || d->n_levels != 1 || pose) return DVF_EUNSUPPORTED;
+      launch_warp_bwd_fused(prm, nb, zeros, cs);
+      return launch_status();
+    }
 #define DVF_DISPATCH_C3(Z)                                                          \
   switch (d->V) {                                                                   \
     case 1: launch_loss_c3<1, Z>(prm, nb, expl, need_grad, tma, cs); break;         \
@@ -309,6 +315,52 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
 #undef DVF_DISPATCH_V
   return launch_status();
 }
+
+// ---- dvf_inverse_warp_bwd without d img, run by the image kernel (dvf_warp.cu decides when) ----------------------------
+namespace dvf {
+static void warp_bwd_as_loss(const dvf_desc* d, dvf_loss_desc& ld, dvf_level& lv) {
+  ld = dvf_loss_desc{};
+  ld.B = d->B;
+  ld.C = 3;
+  ld.V = 1;
+  ld.n_levels = 1;
+  ld.dtype = DVF_F32;
+  ld.layout = DVF_NCHW;
+  ld.padding = d->padding;
+  ld.flags = d->flags & DVF_FLAG_ALIGN_CORNERS;
+  ld.grad_dtype = DVF_F32;
+  lv = dvf_level{};
+  lv.H = d->H;
+  lv.W = d->W;
+}
+bool warp_bwd_fused_ok(const dvf_desc* d, const void* gout, const void* img, const float* depth) {
+  return d->C == 3 && ((long long)d->H * d->W) % 4 == 0 && aligned(gout, 16) && aligned(img, 16) && aligned(depth, 16);
+}
+size_t warp_bwd_fused_workspace_bytes(const dvf_desc* d) {
+  dvf_loss_desc ld;
+  dvf_level lv;
+  warp_bwd_as_loss(d, ld, lv);
+  Plan pl;
+  if (make_plan(&ld, &lv, pl) != DVF_OK) return 0;
+  return pl.bytes + 256;   // + the (unused) loss term of the launch
+}
+int warp_bwd_fused(const dvf_desc* d, const void* gout, const void* img, const float* depth, const float* P, const float* Kinv,
+                   float* gdepth, float* gP, void* workspace, size_t workspace_bytes, void* stream) {
+  dvf_loss_desc ld;
+  dvf_level lv;
+  warp_bwd_as_loss(d, ld, lv);
+  lv.depth = depth;
+  lv.tgt = gout;
+  lv.src[0] = img;
+  lv.P = P;
+  lv.Kinv = Kinv;
+  lv.gdepth = gdepth;
+  lv.gP = gP;
+  if (workspace_bytes < 256) return DVF_EWORKSPACE;
+  float* const term = reinterpret_cast<float*>(static_cast<char*>(workspace) + workspace_bytes - 256);
+  return run_loss(&ld, &lv, nullptr, term, workspace, workspace_bytes - 256, stream, true);
+}
+}  // namespace dvf
 
 DVF_EXPORT int dvf_photo_loss_fused(const dvf_loss_desc* d, const dvf_level* levels, float* terms, void* workspace,
                                     size_t workspace_bytes, void* stream) {

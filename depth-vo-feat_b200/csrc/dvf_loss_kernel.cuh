@@ -433,9 +433,16 @@ constexpr int c3_min_blocks(int views) { return views >= 3 ? 3 : 4; }
 #endif
 // kGlue: the producer glue (disparity -> depth, image scale; dvf_loss_desc) is compiled in.  A separate variant because the
 // three CTA-uniform branches it needs cost the plain path 1.8 % when they are always present (profiles/r2_summary.md).
-template <int kV, bool kZeros, bool kExpl, bool kGrad, bool kTma, bool kGlue = false, int kMinBlocks = c3_min_blocks(kV)>
+//
+// kExt: the three streamed "target" planes hold an UPSTREAM GRADIENT d L / d warped instead of a target image, and nothing
+// of the loss is evaluated: the kernel is then the backward of the materialised warp (dvf_inverse_warp_bwd without d img:
+// inverse_warp.py:160-193 differentiated w.r.t. depth and P) with the ring, the balanced split and the deterministic dL/dP
+// fold of the loss kernel.  V = 1, no masks, one level.
+template <int kV, bool kZeros, bool kExpl, bool kGrad, bool kTma, bool kGlue = false, int kMinBlocks = c3_min_blocks(kV),
+          bool kExt = false>
 __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kernel(const __grid_constant__ LossParams prm) {
   constexpr int kC = 3;
+  static_assert(!kExt || (kV == 1 && !kExpl && kGrad && !kGlue), "kExt: backward of the materialised warp");
 #ifdef DVF_ACC_SMEM
   constexpr bool kAccSmem = kV == 1;
 #else
@@ -728,22 +735,25 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
       }
       const f2 ex = kExpl ? exv[kExpl ? v : 0] : dup(1.0f);
 
-      const f2 wnw = mul2(L.s, L.e), wne = mul2(L.s, L.w), wsw = mul2(L.n, L.e), wse = mul2(L.n, L.w);
       f2 d0[kC], d1[kC];
-      const f2 w0 = bilerp2(t00[0], t01[0], t10[0], t11[0], wnw, wne, wsw, wse);
-      const f2 w1 = bilerp2(t00[1], t01[1], t10[1], t11[1], wnw, wne, wsw, wse);
-      const f2 w2 = bilerp2(t00[2], t01[2], t10[2], t11[2], wnw, wne, wsw, wse);
-      // dead lanes have all-zero taps => any = false
-      const bool anyA = (w0.x != 0.0f) || (w1.x != 0.0f) || (w2.x != 0.0f);
-      const bool anyB = (w0.y != 0.0f) || (w1.y != 0.0f) || (w2.y != 0.0f);
-      d0[0] = sub2(tg0, w0);
-      d0[1] = sub2(tg1, w1);
-      d0[2] = sub2(tg2, w2);
+      bool anyA = true, anyB = true;
+      if (!kExt) {
+        const f2 wnw = mul2(L.s, L.e), wne = mul2(L.s, L.w), wsw = mul2(L.n, L.e), wse = mul2(L.n, L.w);
+        const f2 w0 = bilerp2(t00[0], t01[0], t10[0], t11[0], wnw, wne, wsw, wse);
+        const f2 w1 = bilerp2(t00[1], t01[1], t10[1], t11[1], wnw, wne, wsw, wse);
+        const f2 w2 = bilerp2(t00[2], t01[2], t10[2], t11[2], wnw, wne, wsw, wse);
+        // dead lanes have all-zero taps => any = false
+        anyA = (w0.x != 0.0f) || (w1.x != 0.0f) || (w2.x != 0.0f);
+        anyB = (w0.y != 0.0f) || (w1.y != 0.0f) || (w2.y != 0.0f);
+        d0[0] = sub2(tg0, w0);
+        d0[1] = sub2(tg1, w1);
+        d0[2] = sub2(tg2, w2);
 #pragma unroll
-      for (int c = 0; c < kC; ++c) d1[c] = kExpl ? mul2(d0[c], ex) : d0[c];
-      const float lsA = add(add(fabsf(d1[0].x), fabsf(d1[1].x)), fabsf(d1[2].x));
-      const float lsB = add(add(fabsf(d1[0].y), fabsf(d1[1].y)), fabsf(d1[2].y));
-      accl[v] += (anyA ? lsA : 0.0f) + (anyB ? lsB : 0.0f);
+        for (int c = 0; c < kC; ++c) d1[c] = kExpl ? mul2(d0[c], ex) : d0[c];
+        const float lsA = add(add(fabsf(d1[0].x), fabsf(d1[1].x)), fabsf(d1[2].x));
+        const float lsB = add(add(fabsf(d1[0].y), fabsf(d1[1].y)), fabsf(d1[2].y));
+        accl[v] += (anyA ? lsA : 0.0f) + (anyB ? lsB : 0.0f);
+      }
       if (kGrad) {
         f2 gx = dup(0.0f), gy = dup(0.0f);
         // nsu = -sign(d1)/N (0 where d1 == 0 or the pixel has no valid sample): the gradient of the warped value
@@ -751,6 +761,10 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) photo_loss_c3x2_kern
         f2 nsu[kC];
 #pragma unroll
         for (int c = 0; c < kC; ++c) {
+          if (kExt) {   // the gradient of the warped value comes from the caller (dead lanes: zeroed above)
+            bilerp_grad2(t00[c], t01[c], t10[c], t11[c], L, c == 0 ? tg0 : (c == 1 ? tg1 : tg2), gx, gy);
+            continue;
+          }
           nsu[c] = make_float2(neg_signed_unit(d1[c].x, ngate.x), neg_signed_unit(d1[c].y, ngate.y));
           const f2 ng = kExpl ? mul2(nsu[c], ex) : nsu[c];
           bilerp_grad2(t00[c], t01[c], t10[c], t11[c], L, ng, gx, gy);
@@ -1076,5 +1090,6 @@ template <int kV, bool kZeros>
 void launch_loss_c3(const LossParams& prm, int blocks, bool expl, bool grad, bool tma, cudaStream_t st);
 template <int kV, bool kZeros>
 void launch_loss_cn(const LossParams& prm, int blocks, cudaStream_t st);
+void launch_warp_bwd_fused(const LossParams& prm, int blocks, bool zeros, cudaStream_t st);   // kExt variants (TMA ring only)
 
 }  // namespace dvf

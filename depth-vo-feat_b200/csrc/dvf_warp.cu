@@ -657,10 +657,16 @@ DVF_EXPORT int dvf_inverse_warp_fwd(const dvf_desc* d, const void* img, const fl
   return launch_status();
 }
 
+// Workspace = [partials + counters of the kernels of this file][workspace of the image-kernel route]: the two routes never
+// share a byte, so one buffer serves whichever route a call takes (both leave their counters zero).
+static size_t own_bwd_workspace(const WarpParams& p) {
+  return align_up((size_t)p.blocks_per_image * p.B * kRedSlots * sizeof(float), 256) + align_up((size_t)p.B * sizeof(unsigned), 256);
+}
+
 DVF_EXPORT size_t dvf_inverse_warp_bwd_workspace_bytes(const dvf_desc* d) {
   WarpParams p = {};
   if (fill_params(d, p) != DVF_OK) return 0;
-  return align_up((size_t)p.blocks_per_image * p.B * kRedSlots * sizeof(float), 256) + align_up((size_t)p.B * sizeof(unsigned), 256);
+  return own_bwd_workspace(p) + (p.C == 3 ? warp_bwd_fused_workspace_bytes(d) : 0);
 }
 
 DVF_EXPORT int dvf_inverse_warp_bwd(const dvf_desc* d, const void* gout, const void* img, const float* depth,
@@ -674,6 +680,12 @@ DVF_EXPORT int dvf_inverse_warp_bwd(const dvf_desc* d, const void* gout, const v
   const size_t need = dvf_inverse_warp_bwd_workspace_bytes(d);
   if (!workspace || workspace_bytes < need) return DVF_EWORKSPACE;
   if (!aligned(workspace, 256)) return DVF_EINVAL_ALIGN;
+  // images without d img: the fused loss kernel fed with the upstream gradient (ring of bulk copies, balanced persistent
+  // split: 59 -> see profiles/r2_summary.md); anything it does not cover stays on the kernels of this file
+  if (!gimg && warp_bwd_fused_ok(d, gout, img, depth) && aligned(gdepth, 8)) {
+    const size_t own = own_bwd_workspace(p);
+    return warp_bwd_fused(d, gout, img, depth, P, Kinv, gdepth, gP, static_cast<char*>(workspace) + own, need - own, stream);
+  }
   p.img = static_cast<const float*>(img);
   p.gout = static_cast<const float*>(gout);
   p.depth = depth;

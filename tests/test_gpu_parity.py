@@ -163,6 +163,35 @@ def test_inverse_warp_fwd_bwd_vs_oracle(ops, oracle, syn, case):
     assert_close(npy(gd), ogd, what="gdepth")
     assert_close(npy(gi), ogi, what="gimg")
     assert_close(npy(gP), ogP, what="gP")
+    # without d img, images take the route through the fused loss kernel (TMA ring, balanced split): the same chain
+    _, gd2, gP2 = ops.inverse_warp_bwd_P(cu(gout), cu(img), cu(depth), cu(P), Kinv.cuda(), pad, need_gimg=False)
+    assert np.array_equal(npy(gd2), npy(gd)), "d depth must not depend on the route"
+    assert_close(npy(gP2), ogP, what="gP (no d img)")
+
+
+def test_inverse_warp_bwd_route_and_workspace_reuse(ops, oracle, syn):
+    """dvf_inverse_warp_bwd picks its kernel per call (d img requested or not, alignment): alternating calls on ONE cached
+    workspace, a batch that is cut into many pieces, and an unaligned depth view that falls back to the plain kernel."""
+    B, H, W = 16, 128, 416
+    d, pose = _case(syn, B, 3, H, W, "kitti", True, seed=33)
+    K, Kinv = d["intrinsics"], d["intrinsics_inv"]
+    P = oracle.project(K.numpy(), oracle.pose_vec2mat(pose.numpy()))
+    img, depth = d["img_R1"].numpy(), d["depth"].numpy()
+    gout = np.random.default_rng(2).standard_normal(img.shape).astype(np.float32)
+    _, ogd, ogP = oracle.inverse_warp_bwd_P(gout, img, depth, P, Kinv.numpy(), "zeros", need_gimg=False)
+    args = (cu(gout), cu(img), cu(depth), cu(P), Kinv.cuda(), "zeros")
+    for need in (False, True, False, False, True, False):
+        gi, gd, gP = ops.inverse_warp_bwd_P(*args, need_gimg=need)
+        assert (gi is not None) == need
+        assert np.array_equal(npy(gd), ogd), "d depth is bit-exact on either route"
+        assert_close(npy(gP), ogP, what="gP")
+    # a depth tensor that starts 4 bytes off a 16-byte boundary: no bulk copies, plain kernel, same numbers
+    buf = torch.empty(depth.size + 1, device="cuda")
+    dv = buf[1:].view(depth.shape)
+    dv.copy_(cu(depth))
+    _, gd, gP = ops.inverse_warp_bwd_P(args[0], args[1], dv, args[3], args[4], "zeros", need_gimg=False)
+    assert np.array_equal(npy(gd), ogd)
+    assert_close(npy(gP), ogP, what="gP (unaligned)")
 
 
 @pytest.mark.parametrize("V,with_expl,C,pad", [(1, False, 3, "zeros"), (2, False, 3, "zeros"), (2, True, 3, "zeros"),
