@@ -249,9 +249,27 @@ def cpu_baseline(wl, seconds, B):
         el = time.perf_counter() - t0
         if el >= seconds or n >= 200:
             break
-    return {"value": warped_px(wl, B) * n / el, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} fwd+bwd iterations of the same workload at batch {B} ({warped_px(wl, B)} warped px each), "
-                      f"torch {torch.__version__} CPU, {cores} threads, oracle/torch_port.py"}
+    out = {"value": warped_px(wl, B) * n / el, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{n} fwd+bwd iterations of the same workload at batch {B} ({warped_px(wl, B)} warped px each), "
+                     f"torch {torch.__version__} CPU, {cores} threads, oracle/torch_port.py"}
+    # SURVEY 8(d) also asks for a single-thread figure: a few iterations at a batch that keeps this leg to seconds
+    B1 = max(1, min(B, 8))
+    torch.set_num_threads(1)
+    try:
+        step1 = torch_port_step_fn(wl, B1)
+        step1()
+        n1, t0 = 0, time.perf_counter()
+        while True:
+            step1()
+            n1 += 1
+            el1 = time.perf_counter() - t0
+            if el1 >= min(seconds, 4.0) or n1 >= 20:
+                break
+        out["one_thread"] = {"value": warped_px(wl, B1) * n1 / el1, "unit": UNIT, "cores": 1,
+                             "sample": f"{n1} iterations at batch {B1}"}
+    finally:
+        torch.set_num_threads(cores)
+    return out
 
 
 def run_reference(args):

@@ -208,7 +208,7 @@ static int run_loss(const dvf_loss_desc* d, const dvf_level* levels, const dvf_p
     t.HW = s.H * s.W;
     t.divW = make_fastdiv((uint32_t)s.W);
     t.geo = make_geo(s.H, s.W, (d->flags & DVF_FLAG_ALIGN_CORNERS) != 0);
-    t.allow_fast = (s.W > 1 && s.H > 1 && s.W <= 32768 && s.H <= 32768);
+    t.allow_fast = (s.W > 1 && s.H > 1 && s.W - 1 <= kMaxConstDiv && s.H - 1 <= kMaxConstDiv);
     t.prefetch_rows = s.W <= 512 ? 1 : 0;
     t.ds = pose ? pose->downscale[l] : 1.0f;
     t.inv_n = 1.0f / (float)((double)mean_batch * d->C * s.H * s.W);

@@ -613,7 +613,7 @@ static int fill_params(const dvf_desc* d, WarpParams& p) {
   p.HW = d->H * d->W;
   p.divW = make_fastdiv((uint32_t)d->W);
   p.geo = make_geo(d->H, d->W, (d->flags & DVF_FLAG_ALIGN_CORNERS) != 0);
-  p.allow_fast = d->W > 1 && d->H > 1;
+  p.allow_fast = d->W > 1 && d->H > 1 && d->W - 1 <= kMaxConstDiv && d->H - 1 <= kMaxConstDiv;
   p.zeros_padding = d->padding == DVF_PAD_ZEROS;
   p.blocks_per_image = (p.HW + kThreads * kWarpPPT - 1) / (kThreads * kWarpPPT);
   // backward: about 8 CTAs per SM over the whole batch, each walking several chunks, so that the CTA reduction and
