@@ -33,16 +33,7 @@ __device__ __forceinline__ f2 rcp_refined2(f2 b, f2 nb /* = -b */) {
   const f2 t = fma2(nb, r, dup(1.0f));
   return fma2(r, t, r);
 }
-__device__ __forceinline__ f2 div_by2(f2 a, f2 nb /* = -b */, f2 r) {
-  f2 q = mul2(a, r);
-  f2 e = fma2(nb, q, a);
-  q = fma2(e, r, q);
-  e = fma2(nb, q, a);
-  return fma2(e, r, q);
-}
-
-// division by the per-level constants W-1 / H-1: one correction step (dvf_math.cuh: div_by_const, checked exhaustively)
-__device__ __forceinline__ f2 div_by_const2(f2 a, f2 nb /* = -b */, f2 r) {
+__device__ __forceinline__ f2 div_by2(f2 a, f2 nb /* = -b */, f2 r) {   // one correction step: see dvf_math.cuh: div_by
   const f2 q = mul2(a, r);
   return fma2(fma2(nb, q, a), r, q);
 }
@@ -100,8 +91,8 @@ __device__ __forceinline__ void project2(const float* __restrict__ P /*3x4, broa
   o.u = div_by2(X, o.nZ, o.rZ);
   o.v = div_by2(Y, o.nZ, o.rZ);
   const f2 mone = dup(-1.0f);
-  o.xn = add2(div_by_const2(add2(o.u, o.u), g.nW1, g.rW1), mone);
-  o.yn = add2(div_by_const2(add2(o.v, o.v), g.nH1, g.rH1), mone);
+  o.xn = add2(div_by2(add2(o.u, o.u), g.nW1, g.rW1), mone);
+  o.yn = add2(div_by2(add2(o.v, o.v), g.nH1, g.rH1), mone);
   if (kZeros) {
     o.xn = make_float2(fabsf(o.xn.x) > 1.0f ? 2.0f : o.xn.x, fabsf(o.xn.y) > 1.0f ? 2.0f : o.xn.y);
     o.yn = make_float2(fabsf(o.yn.x) > 1.0f ? 2.0f : o.yn.x, fabsf(o.yn.y) > 1.0f ? 2.0f : o.yn.y);
@@ -173,8 +164,8 @@ __device__ __forceinline__ void chain_backward2(const float* __restrict__ P, con
     gyn = make_float2(p.yn.x == 2.0f ? 0.0f : gyn.x, p.yn.y == 2.0f ? 0.0f : gyn.y);
   }
   const f2 two = dup(2.0f);
-  const f2 gu = mul2(div_by_const2(gxn, g.nW1, g.rW1), two);
-  const f2 gv = mul2(div_by_const2(gyn, g.nH1, g.rH1), two);
+  const f2 gu = mul2(div_by2(gxn, g.nW1, g.rW1), two);
+  const f2 gv = mul2(div_by2(gyn, g.nH1, g.rH1), two);
   const f2 gq0 = div_by2(gu, p.nZ, p.rZ);
   const f2 gq1 = div_by2(gv, p.nZ, p.rZ);
   const f2 uz = div_by2(p.u, p.nZ, p.rZ);

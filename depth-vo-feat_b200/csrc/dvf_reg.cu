@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) explainability_loss_kernel(const __g
         const float den = fmaxf(mul(sub(1.0f, x), x), 1e-12f);        // in [1e-12, 0.25] whatever x is
         float q;
         if (fabsf(num) <= 1e20f) {      // every intermediate of the reciprocal-based sequence stays normal: exact
-          q = div_by(div_by(num, den, rcp_refined(den)), fn, rn);
+          q = div_by_2step(div_by_2step(num, den, rcp_refined(den)), fn, rn);
         } else {                        // absurd inputs, NaN: the plain operator
           q = div(div(num, den), fn);
         }
