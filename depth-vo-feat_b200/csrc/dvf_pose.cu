@@ -11,6 +11,45 @@
 
 namespace dvf {
 
+// ---- REF_CUDA arithmetic profile (DVF_ROT_REF_CUDA or-ed into `rotation`) --------------------
+// The reference run with torch-CUDA eager rounds the pose chain differently from torch-CPU (this library's default target):
+// torch.sin / torch.cos are libdevice's sinf / cosf, and the tiny batched matmuls (xmat @ ymat @ zmat, intrinsics @ pose_mat:
+// cuBLAS) accumulate as an FMA chain, k ascending, instead of multiply / add / add.  Established on the B200 against torch
+// 2.11+cu128 (profiles/ref_cuda_probe2.py: 100 % of the entries for batches up to 256 -- a 200 000-matrix [3,3]@[3,4] batch
+// takes another cuBLAS kernel -- and 100 % of 800 000 angles).  Everything per pixel already rounds alike on both devices
+// (profiles/ref_cuda_probe.py), so the profile lives in this file only: callers that want torch-CUDA's bits compute P with
+// it and hand P to the loss / warp entries (the fused-pose entry evaluates the torch-CPU profile).
+template <int N>
+__device__ __forceinline__ void mm3_fma(const float* a, const float* b, float* out) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+      out[r * N + c] = fma_(a[r * 3 + 2], b[2 * N + c], fma_(a[r * 3 + 1], b[1 * N + c], mul(a[r * 3 + 0], b[0 * N + c])));
+}
+static __device__ __noinline__ void posemat_fwd_ref_cuda(const float* vec, int rotation, float* pm /*3x4*/) {
+  float R[9];
+  if (rotation == DVF_ROT_EULER) {
+    const float x = vec[3], y = vec[4], z = vec[5];
+    const float cz = cosf(z), sz = sinf(z), cy = cosf(y), sy = sinf(y), cx = cosf(x), sx = sinf(x);
+    const float zero = mul(z, 0.0f), one = add(zero, 1.0f);
+    const float zm[9] = {cz, -sz, zero, sz, cz, zero, zero, zero, one};
+    const float ym[9] = {cy, zero, sy, zero, one, zero, -sy, zero, cy};
+    const float xm[9] = {one, zero, zero, zero, cx, -sx, zero, sx, cx};
+    float xy[9];
+    mm3_fma<3>(xm, ym, xy);
+    mm3_fma<3>(xy, zm, R);
+  } else {
+    rotation_fwd(vec + 3, rotation, R);   // quat2mat is elementwise arithmetic: no matmul, no trigonometry
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pm[r * 4 + c] = R[r * 3 + c];
+    pm[r * 4 + 3] = vec[r];
+  }
+}
+
 struct Scales {
   float ds[DVF_MAX_LEVELS];
   int n;
@@ -22,8 +61,11 @@ __global__ void pose_proj_fwd_kernel(const float* __restrict__ vec, const float*
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= B * V) return;
   const int b = n / V;
+  const bool ref_cuda = (rotation & DVF_ROT_REF_CUDA) != 0;
+  rotation &= 0xff;
   float pm[12];
-  posemat_fwd(vec + (size_t)n * 6, rotation, pm);
+  if (ref_cuda) posemat_fwd_ref_cuda(vec + (size_t)n * 6, rotation, pm);
+  else posemat_fwd(vec + (size_t)n * 6, rotation, pm);
   if (posemat) {
 #pragma unroll
     for (int k = 0; k < 12; ++k) posemat[(size_t)n * 12 + k] = pm[k];
@@ -35,7 +77,8 @@ __global__ void pose_proj_fwd_kernel(const float* __restrict__ vec, const float*
   for (int l = 0; l < sc.n; ++l) {
     float Ks[9], Pl[12];
     scaled_K(Kb, sc.ds[l], Ks);
-    mm3<4>(Ks, pm, Pl);
+    if (ref_cuda) mm3_fma<4>(Ks, pm, Pl);
+    else mm3<4>(Ks, pm, Pl);
     if (P) {
 #pragma unroll
       for (int k = 0; k < 12; ++k) P[((size_t)l * B * V + n) * 12 + k] = Pl[k];
@@ -88,7 +131,7 @@ DVF_EXPORT int dvf_pose_proj_fwd(const float* vec, const float* K, const float* 
                                  float* Kinv_s, void* stream) {
   if (!vec) return DVF_EINVAL_NULL;
   if (B <= 0 || V <= 0) return DVF_EINVAL_SHAPE;
-  if (rotation != DVF_ROT_EULER && rotation != DVF_ROT_QUAT) return DVF_EINVAL_DTYPE;
+  if ((rotation & ~DVF_ROT_REF_CUDA) != DVF_ROT_EULER && (rotation & ~DVF_ROT_REF_CUDA) != DVF_ROT_QUAT) return DVF_EINVAL_DTYPE;
   if (!posemat && !P && !Kinv_s) return DVF_EINVAL_NULL;
   if ((P || Kinv_s) && !K) return DVF_EINVAL_NULL;
   if (Kinv_s && !Kinv) return DVF_EINVAL_NULL;
@@ -108,6 +151,7 @@ DVF_EXPORT int dvf_pose_proj_bwd(const float* gP, const float* gposemat, const f
   if (!gP && !gposemat) return DVF_EINVAL_NULL;
   if (gP && !K) return DVF_EINVAL_NULL;
   if (B <= 0 || V <= 0) return DVF_EINVAL_SHAPE;
+  rotation &= ~DVF_ROT_REF_CUDA;   // the backward is analytic in fp64: one form for both profiles
   if (rotation != DVF_ROT_EULER && rotation != DVF_ROT_QUAT) return DVF_EINVAL_DTYPE;
   Scales sc;
   int st = make_scales(downscale, n_levels, sc);

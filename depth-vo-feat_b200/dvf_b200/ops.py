@@ -162,6 +162,21 @@ def _same_device(*tensors):
 # ------------------------------------------------------------------------------------------------
 # pose -> projection
 # ------------------------------------------------------------------------------------------------
+# Arithmetic profile of the pose chain (include/dvf_b200.h: DVF_ROT_REF_CUDA): "ref_cpu" reproduces the reference run on
+# torch-CPU bit for bit (the default, and what the golden vectors pin), "ref_cuda" the reference run with torch-CUDA eager
+# (libdevice sin / cos, FMA-chain tiny matmuls).  With "ref_cuda" the loss runs in its three-launch form (projection
+# matrices from dvf_pose_proj_fwd, loss kernel given P, dvf_pose_proj_bwd), because the single-launch entry evaluates the
+# torch-CPU profile in its prologue.
+ARITHMETIC = "ref_cpu"
+ROT_REF_CUDA = 0x100
+
+
+def _rot(rotation_mode):
+    if ARITHMETIC not in ("ref_cpu", "ref_cuda"):
+        raise DvfError(f"ops.ARITHMETIC = {ARITHMETIC!r}: expected 'ref_cpu' or 'ref_cuda'")
+    return ROTATION[rotation_mode] | (ROT_REF_CUDA if ARITHMETIC == "ref_cuda" else 0)
+
+
 def pose_proj_fwd(vec, K, Kinv, V, rotation_mode, downscales: Sequence[float], want_posemat=False):
     """vec [B*V,6] (b-major) -> (posemat [B*V,3,4] | None, P [L,B*V,3,4] | None, Kinv_s [L,B,3,3] | None)."""
     lib = _lib.load()
@@ -174,7 +189,7 @@ def pose_proj_fwd(vec, K, Kinv, V, rotation_mode, downscales: Sequence[float], w
     Ks = torch.empty(L, B, 3, 3, device=dev, dtype=torch.float32) if (Kinv is not None and L) else None
     ds = (C.c_float * max(L, 1))(*[float(d) for d in downscales])
     with _same_device(vec, K, Kinv):
-        _lib.check(lib.dvf_pose_proj_fwd(_ptr(vec), _ptr(K), _ptr(Kinv), B, V, ROTATION[rotation_mode], ds, L,
+        _lib.check(lib.dvf_pose_proj_fwd(_ptr(vec), _ptr(K), _ptr(Kinv), B, V, _rot(rotation_mode), ds, L,
                                          _ptr(posemat), _ptr(P), _ptr(Ks), _stream()), "dvf_pose_proj_fwd")
     return posemat, P, Ks
 
@@ -533,8 +548,22 @@ class _LossCall:
                 raise DvfError("dvf_photo_loss_workspace_bytes rejected the shapes")
             ws = workspace(nbytes, dev, ("loss", B, Cc, V, cfg.has_expl, self.layout, self.dtype) +
                            tuple(tuple(x.shape[1:]) for x in self.depths))
-            _checked(lib.dvf_photo_loss_fused_pose(C.byref(d), levels, C.byref(pargs), _ptr(terms), _ptr(ws), ws.numel(),
-                                                   _stream()), "dvf_photo_loss_fused_pose", ws)
+            if ARITHMETIC == "ref_cuda":
+                # torch-CUDA's rounding of the pose chain: P / K^-1_s from dvf_pose_proj_fwd, loss kernel given P, pose
+                # backward from the dL/dP it leaves behind (three launches)
+                _, P, Kinv_s = pose_proj_fwd(vec, self.K, self.Kinv, V, cfg.rotation_mode, cfg.downscales)
+                gP = torch.empty(L, B * V, 3, 4, device=dev, dtype=torch.float32) if g_pose is not None else None
+                for l in range(L):
+                    levels[l].P, levels[l].Kinv = P[l].data_ptr(), Kinv_s[l].data_ptr()
+                    if gP is not None:
+                        levels[l].gP = gP[l].data_ptr()
+                _checked(lib.dvf_photo_loss_fused(C.byref(d), levels, _ptr(terms), _ptr(ws), ws.numel(), _stream()),
+                         "dvf_photo_loss_fused", ws)
+                if gP is not None:
+                    g_pose = pose_proj_bwd(gP, None, vec, self.K, V, cfg.rotation_mode, cfg.downscales).view(B, V, 6)
+            else:
+                _checked(lib.dvf_photo_loss_fused_pose(C.byref(d), levels, C.byref(pargs), _ptr(terms), _ptr(ws), ws.numel(),
+                                                       _stream()), "dvf_photo_loss_fused_pose", ws)
             if not want_grads:
                 return terms, None
             for l in range(L):

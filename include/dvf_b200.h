@@ -55,6 +55,12 @@ typedef enum dvf_dtype { DVF_F32 = 0, DVF_BF16 = 1 } dvf_dtype;
 typedef enum dvf_layout { DVF_NCHW = 0, DVF_NHWC = 1 } dvf_layout;
 typedef enum dvf_padding { DVF_PAD_ZEROS = 0, DVF_PAD_BORDER = 1 } dvf_padding;   /* inverse_warp.py:67, train.py:194 */
 typedef enum dvf_rotation { DVF_ROT_EULER = 0, DVF_ROT_QUAT = 1 } dvf_rotation;  /* inverse_warp.py:152-155 */
+/* Arithmetic profile of the pose chain, or-ed into the `rotation` argument of dvf_pose_proj_fwd / _bwd:
+ * default = the reference on torch-CPU (MKL sin / cos, multiply-add-add tiny matmuls); DVF_ROT_REF_CUDA = the reference
+ * on torch-CUDA eager (libdevice sinf / cosf, FMA-chain tiny matmuls).  The per-pixel arithmetic is the same under both,
+ * so a caller who wants torch-CUDA's bits computes P with this flag and passes P to the warp / loss entries;
+ * dvf_photo_loss_fused_pose evaluates the default profile only and rejects the flag (DVF_EINVAL_DTYPE).            */
+#define DVF_ROT_REF_CUDA 0x100
 
 /* Descriptor flags (dvf_desc.flags, dvf_loss_desc.flags); no environment variables are read anywhere. */
 typedef enum dvf_flags {
