@@ -18,6 +18,7 @@ struct WarpParams {
   FastDiv divW;
   Geo geo;
   int allow_fast, zeros_padding;
+  int ref_cuda;           // forward: torch-CUDA's per-pixel rounding (DVF_FLAG_REF_CUDA)
   int blocks_per_image;
   int bwd_blocks_per_image, bwd_iters;   // backward: a CTA walks bwd_iters chunks of 2*kThreads pixels (amortises its reduction)
   const float* img;
@@ -58,6 +59,31 @@ __device__ __forceinline__ void load_PM(const WarpParams& p, int b, float (&P)[1
   for (int k = 0; k < 9; ++k) M[k] = __ldg(p.Kinv + b * 9 + k);
 }
 
+// DVF_FLAG_REF_CUDA: the same pixel as torch-CUDA eager rounds it.  Differences to the torch-CPU chain (established on
+// the B200 against torch 2.11+cu128, tests/test_gpu_api.py::test_ref_cuda_*): `2*(X/Z)/(w-1)` multiplies by the fp32
+// reciprocal of the scalar (ATen BinaryDivTrueKernel.cu: a * (1 / b)), and grid_sample's CUDA kernel forms the weights as
+// (x1 - ix) * (y1 - iy), ... from the corner coordinates instead of from w = ix - x0, e = 1 - w (GridSampler.cu).
+template <bool kZeros>
+__device__ __forceinline__ void ref_cuda_cell(const Proj& pr, const Geo& g, int H, int W, Loc& L, float (&wt)[4]) {
+  float xn = sub(mul(add(pr.u, pr.u), g.rW1), 1.0f);   // g.rW1 = RN(1 / (w-1)) = torch's `1.0f / b`
+  float yn = sub(mul(add(pr.v, pr.v), g.rH1), 1.0f);
+  if (kZeros) {
+    xn = fabsf(xn) > 1.0f ? 2.0f : xn;
+    yn = fabsf(yn) > 1.0f ? 2.0f : yn;
+  }
+  locate<kZeros>(xn, yn, H, W, g, L);                  // cell and predicates; the un-normalisation is the same FMA
+  float ix = fma_(add(xn, 1.0f), g.halfW, g.offs), iy = fma_(add(yn, 1.0f), g.halfH, g.offs);
+  if (!kZeros) {
+    ix = fminf(fmaxf(ix, 0.0f), g.fW1);
+    iy = fminf(fmaxf(iy, 0.0f), g.fH1);
+  }
+  const float x0 = floorf(ix), y0 = floorf(iy), x1 = add(x0, 1.0f), y1 = add(y0, 1.0f);
+  wt[0] = mul(sub(x1, ix), sub(y1, iy));   // nw
+  wt[1] = mul(sub(ix, x0), sub(y1, iy));   // ne
+  wt[2] = mul(sub(x1, ix), sub(iy, y0));   // sw
+  wt[3] = mul(sub(ix, x0), sub(iy, y0));   // se
+}
+
 template <bool kZeros>
 __global__ void __launch_bounds__(kThreads) inverse_warp_fwd_kernel(const __grid_constant__ WarpParams p) {
   const int b = blockIdx.x / p.blocks_per_image;
@@ -79,8 +105,13 @@ __global__ void __launch_bounds__(kThreads) inverse_warp_fwd_kernel(const __grid
     const bool fast = project<false, kZeros>(P, cam, p.geo, pr) && (p.allow_fast != 0);
     if (__builtin_expect(!fast, 0)) pr = warp_project_exact<kZeros>(p.P + b * 12, cam, p.geo);
     locate<kZeros>(pr.xn, pr.yn, H, W, p.geo, L);
+    float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
+    if (p.ref_cuda) {   // launch-uniform
+      float wt[4];
+      ref_cuda_cell<kZeros>(pr, p.geo, H, W, L, wt);
+      wnw = wt[0]; wne = wt[1]; wsw = wt[2]; wse = wt[3];
+    }
     const int o_nw = L.y0 * W + L.x0;
-    const float wnw = mul(L.s, L.e), wne = mul(L.s, L.w), wsw = mul(L.n, L.e), wse = mul(L.n, L.w);
     bool any = false;
     for (int c = 0; c < p.C; ++c) {
       const float* pl = img_b + (size_t)c * HW + o_nw;
@@ -615,6 +646,7 @@ static int fill_params(const dvf_desc* d, WarpParams& p) {
   p.geo = make_geo(d->H, d->W, (d->flags & DVF_FLAG_ALIGN_CORNERS) != 0);
   p.allow_fast = d->W > 1 && d->H > 1 && d->W - 1 <= kMaxConstDiv && d->H - 1 <= kMaxConstDiv;
   p.zeros_padding = d->padding == DVF_PAD_ZEROS;
+  p.ref_cuda = (d->flags & DVF_FLAG_REF_CUDA) != 0;
   p.blocks_per_image = (p.HW + kThreads * kWarpPPT - 1) / (kThreads * kWarpPPT);
   // backward: about 8 CTAs per SM over the whole batch, each walking several chunks, so that the CTA reduction and
   // its ticket are paid once per few thousand pixels
@@ -646,7 +678,7 @@ DVF_EXPORT int dvf_inverse_warp_fwd(const dvf_desc* d, const void* img, const fl
   cudaStream_t cs = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)(p.blocks_per_image * p.B);
   // images: packed pixel pairs (needs an even HW and 8-byte aligned planes); anything else: generic kernel
-  const bool packed = p.C == 3 && p.HW % 2 == 0 && aligned(depth, 8) && aligned(warped, 8) && (!valid || aligned(valid, 2));
+  const bool packed = !p.ref_cuda && p.C == 3 && p.HW % 2 == 0 && aligned(depth, 8) && aligned(warped, 8) && (!valid || aligned(valid, 2));
   if (packed) {
     if (p.zeros_padding) inverse_warp_fwd_c3x2_kernel<true><<<grid, kThreads, 0, cs>>>(p);
     else inverse_warp_fwd_c3x2_kernel<false><<<grid, kThreads, 0, cs>>>(p);
@@ -675,6 +707,7 @@ DVF_EXPORT int dvf_inverse_warp_bwd(const dvf_desc* d, const void* gout, const v
   WarpParams p = {};
   int st = fill_params(d, p);
   if (st != DVF_OK) return st;
+  if (p.ref_cuda) return DVF_EUNSUPPORTED;   // gradients follow torch-CPU (include/dvf_b200.h)
   if (!gout || !img || !depth || !P || !Kinv || !gdepth || !gP) return DVF_EINVAL_NULL;
   if (!aligned(gout, 4) || !aligned(img, 4) || !aligned(depth, 4) || !aligned(gdepth, 4) || !aligned(gP, 4)) return DVF_EINVAL_ALIGN;
   const size_t need = dvf_inverse_warp_bwd_workspace_bytes(d);

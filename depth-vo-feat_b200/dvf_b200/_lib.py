@@ -18,6 +18,7 @@ NCHW, NHWC = 0, 1
 PADDING = {"zeros": 0, "border": 1}
 ROTATION = {"euler": 0, "quat": 1}
 FLAG_ALIGN_CORNERS, FLAG_ZERO_GSRC, FLAG_NAN_CHECK, FLAG_NO_TMA, FLAG_PDL, FLAG_DISPARITY, FLAG_PDL_CHAINED = 1, 2, 4, 8, 16, 32, 64
+FLAG_REF_CUDA = 128   # dvf_inverse_warp_fwd: torch-CUDA's per-pixel rounding
 ABI_VERSION = 2
 
 

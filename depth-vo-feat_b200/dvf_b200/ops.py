@@ -248,6 +248,8 @@ def inverse_warp_fwd_P(img, depth, P, Kinv, padding_mode="zeros", want_valid=Fal
     warped = torch.empty_like(img)
     valid = torch.empty(depth.shape, dtype=torch.uint8, device=img.device) if want_valid else None
     d = _desc(img, padding_mode)
+    if ARITHMETIC == "ref_cuda":
+        d.flags |= _lib.FLAG_REF_CUDA   # forward only: the backward entry follows torch-CPU
     with _same_device(img, depth, P, Kinv):
         _lib.check(lib.dvf_inverse_warp_fwd(C.byref(d), _ptr(img), _ptr(depth), _ptr(P), _ptr(Kinv), _ptr(warped),
                                             _ptr(valid), _stream()), "dvf_inverse_warp_fwd")

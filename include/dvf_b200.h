@@ -57,9 +57,10 @@ typedef enum dvf_padding { DVF_PAD_ZEROS = 0, DVF_PAD_BORDER = 1 } dvf_padding; 
 typedef enum dvf_rotation { DVF_ROT_EULER = 0, DVF_ROT_QUAT = 1 } dvf_rotation;  /* inverse_warp.py:152-155 */
 /* Arithmetic profile of the pose chain, or-ed into the `rotation` argument of dvf_pose_proj_fwd / _bwd:
  * default = the reference on torch-CPU (MKL sin / cos, multiply-add-add tiny matmuls); DVF_ROT_REF_CUDA = the reference
- * on torch-CUDA eager (libdevice sinf / cosf, FMA-chain tiny matmuls).  The per-pixel arithmetic is the same under both,
- * so a caller who wants torch-CUDA's bits computes P with this flag and passes P to the warp / loss entries;
- * dvf_photo_loss_fused_pose evaluates the default profile only and rejects the flag (DVF_EINVAL_DTYPE).            */
+ * on torch-CUDA eager (libdevice sinf / cosf, FMA-chain tiny matmuls).  A caller who wants torch-CUDA's bits computes
+ * P with this flag and passes P to the warp / loss entries (per pixel torch-CUDA differs in two more places, see
+ * DVF_FLAG_REF_CUDA); dvf_photo_loss_fused_pose evaluates the default profile only and rejects the flag
+ * (DVF_EINVAL_DTYPE).                                                                                              */
 #define DVF_ROT_REF_CUDA 0x100
 
 /* Descriptor flags (dvf_desc.flags, dvf_loss_desc.flags); no environment variables are read anywhere. */
@@ -95,7 +96,13 @@ typedef enum dvf_flags {
    * whole GPU -- about 64 units of 256 pixels per CTA, down to one CTA per SM: fewer CTA boundaries = fewer pieces =
    * less fixed cost, and the SM slots one launch leaves free are filled by its neighbours in the stream (C2: 51.4 ->
    * 48.7 us per step).  Sums over CTAs are folded in another order than without the flag (same 1e-7 class).      */
-  DVF_FLAG_PDL_CHAINED = 64
+  DVF_FLAG_PDL_CHAINED = 64,
+  /* dvf_inverse_warp_fwd only: per-pixel arithmetic of the reference run with torch-CUDA eager instead of torch-CPU
+   * (companion of DVF_ROT_REF_CUDA): ATen's CUDA kernels divide by the scalar w-1 / h-1 through a multiplication
+   * by its fp32 reciprocal (BinaryDivTrueKernel.cu) and form the bilinear weights as (x1 - ix) * (y1 - iy)
+   * (GridSampler.cu).  dvf_inverse_warp_bwd rejects it (DVF_EUNSUPPORTED) and the loss entries do not look at it:
+   * gradients and losses follow torch-CPU.                                                                    */
+  DVF_FLAG_REF_CUDA = 128
 } dvf_flags;
 
 /* Image-tensor descriptor shared by the warp and loss entries. */

@@ -421,30 +421,33 @@ def ref_cuda(ops):
         ops.ARITHMETIC = "ref_cpu"
 
 
-@pytest.mark.parametrize("kind", ["kitti", "tiny", "large"])
-def test_ref_cuda_profile_projection_and_warp(ref_cuda, syn, kind):
-    """ops.ARITHMETIC = 'ref_cuda': P = K @ pose_vec2mat(pose) carries the bits of the reference's torch operator sequence
-    executed by torch-CUDA eager (oracle/torch_port.py on the GPU), where the default profile reproduces torch-CPU.  The
-    per-pixel chain keeps torch-CPU's rounding: torch-CUDA divides by the scalar w-1 through a reciprocal multiply
-    (ATen BinaryDivTrueKernel.cu) and forms the bilinear weights as (x1 - ix), so the warped images agree in the validity
-    mask and to ~1e-5 but only 40-70 % of the values are bit-identical (printed)."""
+@pytest.mark.parametrize("padding", ["zeros", "border"])
+@pytest.mark.parametrize("kind,shape", [("kitti", (8, 64, 208)), ("tiny", (8, 64, 208)), ("large", (8, 64, 208)),
+                                        ("kitti", (4, 128, 416))])
+def test_ref_cuda_profile_projection_and_warp(ref_cuda, syn, kind, shape, padding):
+    """ops.ARITHMETIC = 'ref_cuda': P = K @ pose_vec2mat(pose) and the warped image carry the bits of the reference's torch
+    operator sequence executed by torch-CUDA eager (oracle/torch_port.py on this GPU), where the default profile
+    reproduces torch-CPU: libdevice sin / cos and FMA-chain tiny matmuls in the pose chain (DVF_ROT_REF_CUDA), division
+    by the scalar w-1 as a reciprocal multiply and corner-difference bilinear weights per pixel (DVF_FLAG_REF_CUDA)."""
     import inverse_warp as iw
     from oracle import torch_port as tp
     torch.backends.cuda.matmul.allow_tf32 = False
-    B, H, W = 8, 64, 208
+    B, H, W = shape
     d = syn.stereo_temporal_batch(B, H, W, seed=5, temporal=kind)
     t = {k: v.cuda() for k, v in d.items()}
     for pose in (t["T_2to1"], t["T_R2L"]):
         P_ref = t["intrinsics"] @ tp.pose_matrix(pose)
         _, P, _ = ref_cuda.pose_proj_fwd(pose, t["intrinsics"], None, 1, "euler", [1.0])
         assert np.array_equal(npy(P[0]), npy(P_ref)), "projection matrices: torch-CUDA's bits"
-        w_ref = tp.warp(t["img_R1"], t["depth"], pose, t["intrinsics"], t["intrinsics_inv"])
-        w = iw.inverse_warp(t["img_R1"], t["depth"], pose, t["intrinsics"], t["intrinsics_inv"])
-        assert np.array_equal(npy(w != 0), npy(w_ref != 0)), "validity"
-        same = float((w.view(torch.int32) == w_ref.view(torch.int32)).float().mean())
-        err = float((w - w_ref).abs().max())
-        print(f"ref_cuda {kind}: warped image {same * 100:.3f} % bit-identical to torch-CUDA, max |diff| {err:.3e}")
-        assert err <= 2e-4, err   # per-pixel rounding still follows torch-CPU (see the docstring)
+        w_ref = tp.warp(t["img_R1"], t["depth"], pose, t["intrinsics"], t["intrinsics_inv"], padding_mode=padding)
+        w = iw.inverse_warp(t["img_R1"], t["depth"], pose, t["intrinsics"], t["intrinsics_inv"], padding_mode=padding)
+        assert np.array_equal(npy(w), npy(w_ref)), "warped image: torch-CUDA's bits"
+    # and the default profile is NOT torch-CUDA's (otherwise this test would prove nothing)
+    ref_cuda.ARITHMETIC = "ref_cpu"
+    w_cpu_profile = iw.inverse_warp(t["img_R1"], t["depth"], t["T_2to1"], t["intrinsics"], t["intrinsics_inv"], padding_mode=padding)
+    w_ref = tp.warp(t["img_R1"], t["depth"], t["T_2to1"], t["intrinsics"], t["intrinsics_inv"], padding_mode=padding)
+    assert not np.array_equal(npy(w_cpu_profile), npy(w_ref))
+    assert float((w_cpu_profile - w_ref).abs().max()) <= 2e-4
 
 
 def test_ref_cuda_profile_loss_through_the_dropin(ref_cuda, syn):
