@@ -34,15 +34,15 @@ struct RegParams {
   float* out;         // [1] loss value
 };
 
-// sign(v) in {-1, 0, +1}, 0 for NaN.  The smoothness kernel evaluates 38 of these per 4-pixel strip and is bound by the
-// ALU pipe (compares + selects: 66 % busy against 25 % of the FMA pipe), so the sign is formed on the FMA pipe instead:
-// two saturating multiplies by 2^100 take any non-zero magnitude (down to the smallest denormal, 2^-149) to exactly 1,
-// a NaN saturates to 0.
+// sign(v) in {-1, 0, +1}, 0 for NaN.  The smoothness kernel evaluates 44 of these per 4-pixel strip and is bound by
+// instruction issue (78 % of the issue slots busy, profiles/r2_summary.md).  Two instructions: FSET.BF.NE gives 1.0f / 0.0f
+// for an ORDERED v != 0 (false for NaN) and LOP3 copies the sign bit of v onto it.  (Round 1 spent compare + compare +
+// select + select on the ALU pipe; then two saturating multiplies by 2^100 per half on the FMA pipe, five instructions.)
 __device__ __forceinline__ float sgnf(float v) {
-  const float big = 1.2676506e30f;   // 2^100
-  const float p = __saturatef(__saturatef(v * big) * big);
-  const float n = __saturatef(__saturatef(-v * big) * big);
-  return p - n;
+  float nz, r;
+  asm("set.ne.f32.f32 %0, %1, 0f00000000;" : "=f"(nz) : "f"(v));
+  asm("copysign.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(nz));
+  return r;
 }
 
 template <typename F>
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) explainability_loss_kernel(const __g
         const float den = fmaxf(mul(sub(1.0f, x), x), 1e-12f);        // in [1e-12, 0.25] whatever x is
         float q;
         if (fabsf(num) <= 1e20f) {      // every intermediate of the reciprocal-based sequence stays normal: exact
-          q = div_by_2step(div_by_2step(num, den, rcp_refined(den)), fn, rn);
+          q = div_by(div_by(num, den, rcp_refined(den)), fn, rn);   // rn = 1.0f / fn: the correctly rounded reciprocal (dvf_math.cuh)
         } else {                        // absurd inputs, NaN: the plain operator
           q = div(div(num, den), fn);
         }
