@@ -84,7 +84,10 @@ __device__ __forceinline__ void finish_scalar(double local, const RegParams& p, 
 // second difference is evaluated once and shared by the pixels it belongs to -- 28 stencil evaluations per strip
 // instead of 14 per pixel.  Each difference is formed exactly as the reference forms it: a difference of ROUNDED
 // first differences (loss_functions.py:28-33).
-constexpr int kStrip = 4;
+#ifndef DVF_SMOOTH_STRIP   // experiment builds
+#define DVF_SMOOTH_STRIP 4
+#endif
+constexpr int kStrip = DVF_SMOOTH_STRIP;
 
 __device__ __forceinline__ float dd(float a, float b, float c) { return sub(sub(c, b), sub(b, a)); }   // (c-b) - (b-a)
 
