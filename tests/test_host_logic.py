@@ -129,3 +129,23 @@ def test_bench_reference_arm_line_and_config_objects():
     assert d["config"] == bench.config_dict("C1", bench.WORKLOADS["C1"], 1, type("A", (), dict(batch=0, iid_depth=False))())
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["gpu_launches"] == 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
+
+
+def test_arithmetic_profile_selector():
+    """ops.ARITHMETIC picks the rounding profile of the pose chain (include/dvf_b200.h: DVF_ROT_REF_CUDA); anything but the two
+    documented names is an error, and the header, the loader and the binding agree on the flag values."""
+    from dvf_b200 import _lib, ops
+    hdr = open(os.path.join(REPO, "include", "dvf_b200.h")).read()
+    assert int(re.search(r"#define\s+DVF_ROT_REF_CUDA\s+(0x[0-9a-fA-F]+)", hdr).group(1), 16) == ops.ROT_REF_CUDA
+    assert int(re.search(r"DVF_FLAG_REF_CUDA\s*=\s*(\d+)", hdr).group(1)) == _lib.FLAG_REF_CUDA
+    assert ops.ARITHMETIC == "ref_cpu"
+    assert ops._rot("euler") == _lib.ROTATION["euler"] and ops._rot("quat") == _lib.ROTATION["quat"]
+    try:
+        ops.ARITHMETIC = "ref_cuda"
+        assert ops._rot("euler") == (_lib.ROTATION["euler"] | ops.ROT_REF_CUDA)
+        assert ops._rot("quat") == (_lib.ROTATION["quat"] | ops.ROT_REF_CUDA)
+        ops.ARITHMETIC = "fast"
+        with pytest.raises(_lib.DvfError):
+            ops._rot("euler")
+    finally:
+        ops.ARITHMETIC = "ref_cpu"
