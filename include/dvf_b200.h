@@ -167,7 +167,10 @@ size_t dvf_inverse_warp_bwd_workspace_bytes(const dvf_desc* d);
 
 /* gout = dL/dwarped.  gdepth [B,H,W] and gP [B,3,4] are written; gimg
  * (nullable, same dtype/layout as img, fp32 only) is ACCUMULATED into and must
- * be zero-filled by the caller.                                              */
+ * be zero-filled by the caller.  With gimg == NULL, C == 3, H*W % 4 == 0 and
+ * 16-byte aligned gout / img / depth the call runs on the image kernel of the
+ * fused loss (bulk-copy ring, balanced persistent grid); d depth is bit-identical
+ * on either route and the workspace serves both.                              */
 int dvf_inverse_warp_bwd(const dvf_desc* d, const void* gout, const void* img,
                          const float* depth, const float* P, const float* Kinv,
                          float* gdepth, float* gP, void* gimg, void* workspace,
