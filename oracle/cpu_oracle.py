@@ -19,7 +19,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libdvf_oracle.so")
 
-PAD = {"zeros": 0, "border": 1, "zeros_align": 2, "border_align": 3}   # *_align: grid_sample(align_corners=True)
+PAD = {"zeros": 0, "border": 1, "zeros_align": 2, "border_align": 3,   # *_align: grid_sample(align_corners=True)
+       "zeros_cuda": 4, "border_cuda": 5}   # *_cuda: torch-CUDA's per-pixel rounding (forward only, DVFO_REF_CUDA)
 ROT = {"euler": 0, "quat": 1}
 
 

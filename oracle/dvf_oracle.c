@@ -188,6 +188,13 @@ static inline void chain_fwd(const float *P /*3x4*/, const float *M /*3x3*/,
   /* 2*(X/Z)/(w-1) - 1 : exact doubling, TRUE division by float(w-1), subtract */
   o->xn = (2.0f * o->u) / (float)(W - 1) - 1.0f;
   o->yn = (2.0f * o->v) / (float)(H - 1) - 1.0f;
+  if (padding & 4 /* DVFO_REF_CUDA, defined below */) {
+    /* torch-CUDA eager: division by a python scalar = multiplication by its fp32 reciprocal
+     * (ATen/native/cuda/BinaryDivTrueKernel.cu: a * (1 / b)) */
+    const float rw = 1.0f / (float)(W - 1), rh = 1.0f / (float)(H - 1);
+    o->xn = (2.0f * o->u) * rw - 1.0f;
+    o->yn = (2.0f * o->v) * rh - 1.0f;
+  }
   o->mx = o->my = 0;
   if ((padding & 1) == DVFO_PAD_ZEROS) {
     if (o->xn > 1.0f || o->xn < -1.0f) { o->xn = 2.0f; o->mx = 1; }
@@ -203,11 +210,18 @@ typedef struct {
   float gmx, gmy;     /* d ix / d x_n  (size/2, or 0 where border-clipped)  */
   int x0, y0;         /* floor                                             */
   float w, e, n, s;   /* w = ix-x0, e = 1-w, n = iy-y0, s = 1-n            */
+  int cuda_w;         /* DVFO_REF_CUDA: tap weights formed as ATen's CUDA kernel forms them */
+  float cw[4];        /* nw, ne, sw, se                                     */
 } samp_loc;
 
 /* padding arguments carry the grid_sample convention in bit 1: DVFO_ALIGN_CORNERS = align_corners=True (the torch <= 1.2
  * behaviour the reference was written for; ATen ComputeLocation: (x+1) * ((size-1)/2), one rounded product) */
 #define DVFO_ALIGN_CORNERS 2
+/* bit 2: DVFO_REF_CUDA = the per-pixel rounding of the reference run with torch-CUDA eager (forward only; PARITY PINNED by
+ * tests/golden/ref_cuda_warp.npz, produced on a B200 by oracle/gen_golden_ref_cuda.py from torch-CUDA itself): scalar
+ * division as a reciprocal multiply (chain_fwd) and the bilinear weights of ATen/native/cuda/GridSampler.cu,
+ * nw = (x1 - ix) * (y1 - iy), ne = (ix - x0) * (y1 - iy), sw = (x1 - ix) * (iy - y0), se = (ix - x0) * (iy - y0). */
+#define DVFO_REF_CUDA 4
 static inline float unnormalize(float c, int size, int align_corners) {
   if (align_corners) return (c + 1.0f) * ((float)(size - 1) / 2.0f);
   return fmaf(c + 1.0f, (float)size / 2.0f, -0.5f);
@@ -233,6 +247,14 @@ static inline void locate(float xn, float yn, int H, int W, int padding,
   L->e = 1.0f - L->w;
   L->n = L->iy - fy;
   L->s = 1.0f - L->n;
+  L->cuda_w = (padding & DVFO_REF_CUDA) != 0;
+  if (L->cuda_w) {
+    const float x1 = fx + 1.0f, y1 = fy + 1.0f;
+    L->cw[0] = (x1 - L->ix) * (y1 - L->iy);
+    L->cw[1] = (L->ix - fx) * (y1 - L->iy);
+    L->cw[2] = (x1 - L->ix) * (L->iy - fy);
+    L->cw[3] = (L->ix - fx) * (L->iy - fy);
+  }
   /* NaN / huge coordinates: every tap is out of bounds */
   if (!(fx >= -2.0f && fx <= (float)W + 1.0f)) fx = -2.0f;
   if (!(fy >= -2.0f && fy <= (float)H + 1.0f)) fy = -2.0f;
@@ -286,6 +308,7 @@ static inline int sample_px(const float *img_b /*[C,H,W]*/, int C, int H, int W,
   int bnw = inb(x0, y0, H, W), bne = inb(x1, y0, H, W);
   int bsw = inb(x0, y1, H, W), bse = inb(x1, y1, H, W);
   float wnw = L->s * L->e, wne = L->s * L->w, wsw = L->n * L->e, wse = L->n * L->w;
+  if (L->cuda_w) { wnw = L->cw[0]; wne = L->cw[1]; wsw = L->cw[2]; wse = L->cw[3]; }
   int any = 0;
   for (int c = 0; c < C; ++c) {
     const float *pl = img_b + (size_t)c * H * W;

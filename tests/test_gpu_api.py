@@ -450,6 +450,22 @@ def test_ref_cuda_profile_projection_and_warp(ref_cuda, syn, kind, shape, paddin
     assert float((w_cpu_profile - w_ref).abs().max()) <= 2e-4
 
 
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+def test_ref_cuda_profile_golden(ref_cuda, syn, pad):
+    """the committed torch-CUDA fixture (tests/golden/ref_cuda_warp.npz, also what pins the CPU oracle's restatement):
+    projection matrices from the pose and warped images through the drop-in, bit for bit"""
+    import inverse_warp as iw
+    from helpers import golden
+    g = golden("ref_cuda_warp")
+    d = syn.stereo_temporal_batch(int(g["B"]), int(g["H"]), int(g["W"]), seed=int(g["seed"]))
+    t = {k: v.cuda() for k, v in d.items()}
+    for tag, pose in (("temporal", "T_2to1"), ("stereo", "T_R2L")):
+        _, P, _ = ref_cuda.pose_proj_fwd(t[pose], t["intrinsics"], None, 1, "euler", [1.0])
+        assert np.array_equal(npy(P[0]), g["P_" + tag])
+        w = iw.inverse_warp(t["img_R1"], t["depth"], t[pose], t["intrinsics"], t["intrinsics_inv"], padding_mode=pad)
+        assert np.array_equal(npy(w), g[f"warped_{tag}_{pad}"])
+
+
 def test_ref_cuda_profile_loss_through_the_dropin(ref_cuda, syn):
     """the multi-scale loss and its gradients under the torch-CUDA profile (three-launch form) against torch-CUDA autograd"""
     import loss_functions_sfm as sfm

@@ -180,3 +180,24 @@ def test_ssim_oracle_matches_torch_restatement(oracle):
         loss, gy = oracle.ssim_loss(x.numpy(), y.numpy(), None if v is None else v.numpy())
         assert abs(loss - ref.item()) <= 1e-9 + 1e-7 * abs(ref.item())
         assert_close(gy, yd.grad.numpy(), tol=1e-6, what="d loss / d y")
+
+
+@pytest.mark.parametrize("pad", ["zeros", "border"])
+@pytest.mark.parametrize("tag", ["temporal", "stereo"])
+def test_ref_cuda_profile_golden(oracle, tag, pad):
+    """The oracle's DVFO_REF_CUDA restatement of the per-pixel chain (scalar division as a reciprocal multiply, corner-
+    difference bilinear weights) against what torch-CUDA eager produced on a B200 for the reference's operator sequence
+    (tests/golden/ref_cuda_warp.npz, oracle/gen_golden_ref_cuda.py): bit-identical given torch-CUDA's own P -- and the
+    default (torch-CPU) profile is measurably not."""
+    import hashlib
+    from dvf_b200 import synthetic as syn
+    g = golden("ref_cuda_warp")
+    d = syn.stereo_temporal_batch(int(g["B"]), int(g["H"]), int(g["W"]), seed=int(g["seed"]))
+    sha = [hashlib.sha256(np.ascontiguousarray(d[k].numpy()).tobytes()).hexdigest() for k in sorted(d)]
+    assert sha == list(g["inputs_sha"]), "synthetic generator drifted: regenerate the golden on a GPU box"
+    img, depth, Kinv = d["img_R1"].numpy(), d["depth"].numpy(), d["intrinsics_inv"].numpy()
+    ref = g[f"warped_{tag}_{pad}"]
+    w, _ = oracle.inverse_warp_P(img, depth, g["P_" + tag], Kinv, pad + "_cuda")
+    assert np.array_equal(w, ref), "REF_CUDA per-pixel restatement must reproduce torch-CUDA bit for bit"
+    w_cpu, _ = oracle.inverse_warp_P(img, depth, g["P_" + tag], Kinv, pad)
+    assert not np.array_equal(w_cpu, ref) and rel_err(w_cpu, ref) < 1e-4
