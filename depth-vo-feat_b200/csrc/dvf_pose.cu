@@ -40,7 +40,9 @@ static __device__ __noinline__ void posemat_fwd_ref_cuda(const float* vec, int r
     mm3_fma<3>(xm, ym, xy);
     mm3_fma<3>(xy, zm, R);
   } else {
-    rotation_fwd(vec + 3, rotation, R);   // quat2mat is elementwise arithmetic: no matmul, no trigonometry
+    // quat2mat has no matmul and no trigonometry, but torch-CUDA sums the norm in another order: 91 % of the entries agree
+    // (profiles/ref_cuda_quat_probe.py) -- not part of the verified profile
+    rotation_fwd(vec + 3, rotation, R);
   }
 #pragma unroll
   for (int r = 0; r < 3; ++r) {

@@ -60,7 +60,9 @@ typedef enum dvf_rotation { DVF_ROT_EULER = 0, DVF_ROT_QUAT = 1 } dvf_rotation; 
  * on torch-CUDA eager (libdevice sinf / cosf, FMA-chain tiny matmuls).  A caller who wants torch-CUDA's bits computes
  * P with this flag and passes P to the warp / loss entries (per pixel torch-CUDA differs in two more places, see
  * DVF_FLAG_REF_CUDA); dvf_photo_loss_fused_pose evaluates the default profile only and rejects the flag
- * (DVF_EINVAL_DTYPE).                                                                                              */
+ * (DVF_EINVAL_DTYPE).  Verified bit for bit for DVF_ROT_EULER (the reference's default and what its callers use); under
+ * DVF_ROT_QUAT torch-CUDA's quat2mat agrees on ~91 % of the entries only (profiles/ref_cuda_quat_probe.py: its norm
+ * reduction sums in another order) -- quaternion poses keep the torch-CPU rounding of that step.                    */
 #define DVF_ROT_REF_CUDA 0x100
 
 /* Descriptor flags (dvf_desc.flags, dvf_loss_desc.flags); no environment variables are read anywhere. */
